@@ -1,0 +1,212 @@
+/*
+ * uqs_mapping.h -- C ABI of the B200-native post-flight 2D mapping path.
+ *
+ * This header is the drop-in boundary for ONE path of exie1122/micro-quad-SLAM:
+ * poses -> ToF beam ray-cast -> int8 log-odds occupancy grid, i.e. the block
+ * uav_local_nav.c:181-306 as driven from log_tick() at uav_local_nav.c:1629-1635.
+ * All of it runs as hand-written CUDA for sm_100a inside libuqs_mapping.so; there
+ * is no CPU implementation in the library and every entry point fails (returns
+ * non-zero / becomes a no-op with uqs_last_error() set) when no CUDA device is
+ * usable.
+ *
+ * Two groups of symbols:
+ *
+ *  (1) DROP-IN symbols -- same names, types and argument meaning as the
+ *      reference's file-static mapping symbols, so uav_local_nav.c can be built
+ *      with lines 181-385 removed and this header included instead
+ *      (see INTEGRATION.md).  Reference failure behaviour is kept: they are
+ *      silent no-ops when !map_inited or when a ray is off-grid.
+ *
+ *  (2) BATCH symbols (uqs_*) -- what a post-flight replay harness calls: whole
+ *      logs, many flights, device-resident or host buffers, explicit errors.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types appear here.
+ */
+#ifndef UQS_MAPPING_H
+#define UQS_MAPPING_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Geometry and sensor constants.  In the reference these are compile-time   */
+/* #defines / static consts; here they are one runtime struct.               */
+/* ------------------------------------------------------------------------ */
+typedef struct uqs_params {
+  int32_t W, H;          /* MAP_W, MAP_H                     uav_local_nav.c:185-186 */
+  float   res_m;         /* MAP_RES_M                        uav_local_nav.c:182     */
+  float   size_m;        /* MAP_SIZE_M (recentering only)    uav_local_nav.c:183     */
+  float   origin_x;      /* map_origin_x: world x at cell W/2   uav_local_nav.c:191  */
+  float   origin_y;      /* map_origin_y: world y at cell H/2   uav_local_nav.c:192  */
+  float   max_range_m;   /* TOF_MAX_RANGE_M = 4.00f          uav_local_nav.c:117     */
+  float   fov_deg;       /* TOF_FOV_DEG = 63.0f              uav_local_nav.c:118     */
+  float   min_range_m;   /* the 0.05f literal in `dist <= 0.05f`   uav_local_nav.c:290 */
+  float   hit_margin_m;  /* the 0.05f literal in `MAX - 0.05f`     uav_local_nav.c:292 */
+  int32_t lo_free;       /* LO_FREE_DEC = 1                  uav_local_nav.c:194     */
+  int32_t lo_occ;        /* LO_OCC_INC  = 6                  uav_local_nav.c:195     */
+  int32_t lo_min;        /* LO_MIN = -80                     uav_local_nav.c:196     */
+  int32_t lo_max;        /* LO_MAX = +80                     uav_local_nav.c:197     */
+} uqs_params;
+
+/* The reference's own constants (500x500 @ 0.10 m, origin to be set by caller). */
+void uqs_params_default(uqs_params* p);
+
+#define UQS_BEAMS_PER_FRAME 32   /* 4 directions x TOF_COLS(8), uav_local_nav.c:105,286-287 */
+
+/* Error codes returned by uqs_* batch calls (0 = ok). */
+enum {
+  UQS_OK = 0,
+  UQS_ERR_NO_DEVICE = 1,     /* no CUDA device / driver: nothing can run          */
+  UQS_ERR_CUDA = 2,          /* a CUDA call or kernel failed; see uqs_last_error() */
+  UQS_ERR_BAD_ARG = 3,       /* NULL pointer, non-positive size, bad params        */
+  UQS_ERR_NOT_INIT = 4,      /* uqs_init() has not succeeded                       */
+  UQS_ERR_DOMAIN = 5,        /* an input left the domain the exact arithmetic covers
+                                (|angle| >= 120 rad or ray longer than 1024 cells) */
+  UQS_ERR_NOMEM = 6
+};
+
+/* Counters returned by the replay calls.  All exact integers. */
+typedef struct uqs_stats {
+  uint64_t ray_cell_updates;  /* U = sum over accepted rays of max(|dgx|,|dgy|)+1:
+                                 iterations of the while(1) at uav_local_nav.c:254-277 */
+  uint64_t rays_accepted;     /* rays that reached raycast_update with both ends on grid */
+  uint64_t rays_skipped;      /* NaN / <= min_range (:289-290) or off-grid (:243-244)   */
+  uint64_t frames;            /* map_update_from_beams calls replayed                   */
+  uint64_t domain_errors;     /* rays dropped because of UQS_ERR_DOMAIN (should be 0)   */
+} uqs_stats;
+
+/* ------------------------------------------------------------------------ */
+/* (2) Batch API                                                             */
+/* ------------------------------------------------------------------------ */
+
+/* Select a CUDA device, create the library's stream and scratch allocator.
+ * Returns UQS_ERR_NO_DEVICE if none is available (there is no fallback). */
+int  uqs_init(int device);
+void uqs_shutdown(void);
+const char* uqs_last_error(void);
+int  uqs_device_sm_count(void);
+
+/* Run all subsequent work on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL is the legacy default stream).  uqs_use_own_stream() goes back to the
+ * library's own stream.  Lets a host time the kernels
+ * with its own events. */
+int  uqs_set_stream(void* cuda_stream);
+int  uqs_use_own_stream(void);
+/* Number of kernels this library has launched so far (bench.py's gpu_launches). */
+unsigned long long uqs_kernel_launches(void);
+/* Block until everything enqueued so far has finished. */
+int  uqs_sync(void);
+
+/* Kernel tuning knobs (0 keeps the built-in choice).  sub-tile = the square of
+ * cells one warp owns in shared memory; time_slices > 1 splits a flight's frames
+ * into contiguous slices that are replayed concurrently and composed exactly. */
+int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
+
+/*
+ * P0 -- dead-reckoning pose integration (BUILDER-DEFINED: the reference has no
+ * such stage; spec in DESIGN.md section "P0", mirrors uav_local_nav.c:943,1151-1164).
+ * Arrays are [n_flights][n_samples], row-major.  x_out/y_out get the pose of
+ * every sample; x[0]=y[0]=0.
+ *   mode 0: exact -- increments in parallel, summation replayed in sample order
+ *           (bit-identical to the CPU statement of the spec)
+ *   mode 1: scan  -- decoupled-lookback prefix scan in binary64 (throughput
+ *           variant; differs from mode 0 by the fp32 rounding of the serial sum)
+ */
+int uqs_pose_integrate(int n_flights, int n_samples,
+                       const uint32_t* t_ms, const float* of_rate_x, const float* of_rate_y,
+                       const float* h_m, const float* yaw_deg, const uint8_t* of_q,
+                       float* x_out, float* y_out, int mode);
+
+/*
+ * Replay n_flights independent logs of n_frames frames each into n_flights
+ * grids of W*H int8 (row-major, k = gy*W + gx, uav_local_nav.c:216), each
+ * starting from all-zero (uav_local_nav.c:2190).  For every frame this is
+ * exactly map_update_from_beams(x, y, yaw_deg) (uav_local_nav.c:280-306) with
+ * tof_beams_m = ranges[frame][0..31] (direction-major F,R,B,L x 8 columns).
+ * Host buffers; H2D/D2H copies are part of the call.
+ *   x, y, yaw_deg : [n_flights][n_frames]      ranges : [n_flights][n_frames][32]
+ *   grids_out     : [n_flights][H][W] int8
+ */
+int uqs_replay(const uqs_params* p, int n_flights, int n_frames,
+               const float* x, const float* y, const float* yaw_deg, const float* ranges,
+               int8_t* grids_out, uqs_stats* stats);
+
+/* Same, with every pointer a DEVICE pointer on the device given to uqs_init().
+ * accumulate != 0 continues from the grids' current contents instead of zero
+ * (used for chained replays and by the drop-in symbols).  row0/rows restrict
+ * the update to grid rows [row0, row0+rows) -- the tile a GPU owns when one
+ * large grid is split across GPUs; pass 0, H for the whole grid.  grids_dev
+ * always addresses full W*H grids.  Asynchronous on the current stream; stats
+ * (host pointer, may be NULL) is filled after an internal sync only if given. */
+int uqs_replay_dev(const uqs_params* p, int n_flights, int n_frames,
+                   const float* x_dev, const float* y_dev, const float* yaw_dev,
+                   const float* ranges_dev, int8_t* grids_dev,
+                   int accumulate, int row0, int rows, uqs_stats* stats);
+
+/* P0 followed by the replay, one frame per flow sample (frame i uses pose i and
+ * yaw_deg[i]).  Host buffers.  poses_out_x/y may be NULL. */
+int uqs_replay_flow(const uqs_params* p, int n_flights, int n_samples,
+                    const uint32_t* t_ms, const float* of_rate_x, const float* of_rate_y,
+                    const float* h_m, const float* yaw_deg, const uint8_t* of_q,
+                    const float* ranges, int8_t* grids_out,
+                    float* poses_out_x, float* poses_out_y, uqs_stats* stats);
+
+/* Device-pointer form of uqs_pose_integrate (asynchronous on the current stream). */
+int uqs_pose_integrate_dev(int n_flights, int n_samples,
+                           const uint32_t* t_ms, const float* of_rate_x, const float* of_rate_y,
+                           const float* h_m, const float* yaw_deg, const uint8_t* of_q,
+                           float* x_out, float* y_out, int mode);
+
+/* Batched world_to_grid / beam end-points on the device (host buffers), used by
+ * the parity tests to compare cell indices one by one with the reference.
+ *   cells_out : [n][32][2] int32 end cell (gx,gy) or (-1,-1) when the ray is skipped
+ *   origin_out: [n][2] int32 start cell or (-1,-1) */
+int uqs_beam_cells(const uqs_params* p, int n_frames,
+                   const float* x, const float* y, const float* yaw_deg, const float* ranges,
+                   int32_t* cells_out, int32_t* origin_out);
+
+/* Device evaluation of the glibc-2.39 sincosf restatement for n host floats
+ * (parity test hook for SURVEY.md Appendix B). */
+int uqs_sincosf_batch(size_t n, const float* ang, float* sin_out, float* cos_out);
+
+/* Measured on-chip read-modify-write ceiling: every warp of a full grid does
+ * conflict-free byte RMWs on its shared-memory sub-tile.  Returns updates/s. */
+int uqs_measure_rmw_peak(double* updates_per_s);
+
+/* ------------------------------------------------------------------------ */
+/* (1) Drop-in symbols (replace uav_local_nav.c:188-192, 205-216, 229, 241-306) */
+/* ------------------------------------------------------------------------ */
+
+/* Must be called once before the drop-in symbols are used: allocates the
+ * device grid and the pinned host mirror `occ_grid` for a W x H map.
+ * (The reference's arrays are static; a shared library needs an allocator.) */
+int  uqs_dropin_configure(const uqs_params* p);
+/* Replaces `memset(occ_grid, 0, sizeof(occ_grid))` at uav_local_nav.c:2190
+ * (sizeof of a pointer would silently be 8). */
+void map_reset(void);
+/* Make every update enqueued so far visible in occ_grid (host).  Called
+ * implicitly by frontier_score_dir(); call it before reading occ_grid[]. */
+void uqs_dropin_flush(void);
+/* Push a caller-edited occ_grid[] back to the device copy (after direct host writes). */
+int  uqs_dropin_upload(void);
+
+extern int8_t*  occ_grid;            /* W*H int8, row-major, host-visible mirror   (:188) */
+extern bool     map_inited;          /*                                            (:190) */
+extern float    map_origin_x;        /*                                            (:191) */
+extern float    map_origin_y;        /*                                            (:192) */
+extern float    tof_beams_m[4][8];   /* written by the caller before each update   (:108) */
+extern uint8_t  pending_kf_flags;    /* |= KF_MAP_RECENTER (1u<<5) on recenter     (:229) */
+
+bool world_to_grid(float x, float y, int* gx, int* gy);                          /* :205 */
+void raycast_update(float x0, float y0, float x1, float y1, bool hit_occ);       /* :241 */
+void map_update_from_beams(float x_m, float y_m, float yaw_deg);                 /* :280 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UQS_MAPPING_H */

@@ -1,0 +1,308 @@
+"""micro-quad-slam_b200 -- Python binding of libuqs_mapping.so (the product is the C/CUDA library).
+
+The host side of the path is plain C behind ``include/uqs_mapping.h``; this module
+only loads that shared library with ctypes so that pytest and ``bench.py`` can call the
+same C ABI a C harness would.  Function names and argument meaning follow the
+reference's mapping symbols (``uav_local_nav.c:205-306``) and the batch entry points of
+the header.  There is no Python or CPU implementation of the path in here: if the
+library is missing or no CUDA device is usable, calls raise ``UqsError``.
+
+The directory name contains hyphens, so import it with
+``importlib.import_module("micro-quad-slam_b200")``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libuqs_mapping.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libuqs_synth.so")
+
+BEAMS_PER_FRAME = 32
+
+OK, ERR_NO_DEVICE, ERR_CUDA, ERR_BAD_ARG, ERR_NOT_INIT, ERR_DOMAIN, ERR_NOMEM = range(7)
+
+
+class UqsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"uqs error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """``uqs_params`` -- run-time form of the reference's grid/sensor constants."""
+
+    _fields_ = [
+        ("W", C.c_int32), ("H", C.c_int32),
+        ("res_m", C.c_float), ("size_m", C.c_float),
+        ("origin_x", C.c_float), ("origin_y", C.c_float),
+        ("max_range_m", C.c_float), ("fov_deg", C.c_float),
+        ("min_range_m", C.c_float), ("hit_margin_m", C.c_float),
+        ("lo_free", C.c_int32), ("lo_occ", C.c_int32), ("lo_min", C.c_int32), ("lo_max", C.c_int32),
+    ]
+
+    def copy(self) -> "Params":
+        q = Params()
+        C.memmove(C.byref(q), C.byref(self), C.sizeof(Params))
+        return q
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("ray_cell_updates", C.c_uint64), ("rays_accepted", C.c_uint64), ("rays_skipped", C.c_uint64),
+        ("frames", C.c_uint64), ("domain_errors", C.c_uint64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+def make_params(W: int, H: int, res_m: float, size_m: Optional[float] = None, origin=(0.0, 0.0)) -> Params:
+    """Reference defaults (uav_local_nav.c:117-118, 194-197) with the given geometry."""
+    p = Params()
+    p.W, p.H = int(W), int(H)
+    p.res_m = np.float32(res_m)
+    p.size_m = np.float32(size_m if size_m is not None else W * res_m)
+    p.origin_x, p.origin_y = np.float32(origin[0]), np.float32(origin[1])
+    p.max_range_m, p.fov_deg = 4.0, 63.0
+    p.min_range_m, p.hit_margin_m = np.float32(0.05), np.float32(0.05)
+    p.lo_free, p.lo_occ, p.lo_min, p.lo_max = 1, 6, -80, 80
+    return p
+
+
+_lib = None
+
+_EXPORTS = [
+    # batch API
+    "uqs_params_default", "uqs_init", "uqs_shutdown", "uqs_last_error", "uqs_device_sm_count",
+    "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_kernel_launches",
+    "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
+    "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
+    # drop-in symbols
+    "uqs_dropin_configure", "uqs_dropin_flush", "uqs_dropin_upload", "map_reset",
+    "occ_grid", "map_inited", "map_origin_x", "map_origin_y", "tof_beams_m", "pending_kf_flags",
+    "world_to_grid", "raycast_update", "map_update_from_beams",
+]
+
+
+def exported_symbols():
+    return list(_EXPORTS)
+
+
+def lib() -> C.CDLL:
+    """Load libuqs_mapping.so (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UqsError(ERR_NO_DEVICE, f"{LIB_PATH} is missing: build it (python -c 'import __graft_entry__ as g; "
+                       "g.build()'); there is no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    fp, ip, vp = C.POINTER(C.c_float), C.c_int, C.c_void_p
+    L.uqs_last_error.restype = C.c_char_p
+    L.uqs_init.argtypes = [ip]
+    L.uqs_set_stream.argtypes = [vp]
+    L.uqs_set_tuning.argtypes = [ip, ip, ip]
+    L.uqs_kernel_launches.restype = C.c_ulonglong
+    L.uqs_pose_integrate.argtypes = [ip, ip] + [vp] * 8 + [ip]
+    L.uqs_pose_integrate_dev.argtypes = [ip, ip] + [vp] * 8 + [ip]
+    L.uqs_replay.argtypes = [C.POINTER(Params), ip, ip, vp, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.uqs_replay_dev.argtypes = [C.POINTER(Params), ip, ip, vp, vp, vp, vp, vp, ip, ip, ip, C.POINTER(Stats)]
+    L.uqs_replay_flow.argtypes = [C.POINTER(Params), ip, ip] + [vp] * 10 + [C.POINTER(Stats)]
+    L.uqs_beam_cells.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp]
+    L.uqs_sincosf_batch.argtypes = [C.c_size_t, vp, vp, vp]
+    L.uqs_measure_rmw_peak.argtypes = [C.POINTER(C.c_double)]
+    L.uqs_dropin_configure.argtypes = [C.POINTER(Params)]
+    L.world_to_grid.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.world_to_grid.restype = C.c_bool
+    L.raycast_update.argtypes = [C.c_float] * 4 + [C.c_bool]
+    L.raycast_update.restype = None
+    L.map_update_from_beams.argtypes = [C.c_float] * 3
+    L.map_update_from_beams.restype = None
+    L.map_reset.restype = None
+    L.uqs_dropin_flush.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != OK:
+        raise UqsError(rc, lib().uqs_last_error().decode(errors="replace"))
+
+
+def init(device: int = 0):
+    _check(lib().uqs_init(int(device)))
+
+
+def shutdown():
+    lib().uqs_shutdown()
+
+
+def sync():
+    _check(lib().uqs_sync())
+
+
+def set_stream(ptr: Optional[int]):
+    """Run on the given cudaStream_t (int handle; 0 = legacy default stream); None = library stream."""
+    if ptr is None:
+        _check(lib().uqs_use_own_stream())
+    else:
+        _check(lib().uqs_set_stream(C.c_void_p(ptr)))
+
+
+def set_tuning(subtile_w: int = 0, subtile_h: int = 0, time_slices: int = 0):
+    _check(lib().uqs_set_tuning(subtile_w, subtile_h, time_slices))
+
+
+def kernel_launches() -> int:
+    return int(lib().uqs_kernel_launches())
+
+
+def sm_count() -> int:
+    return int(lib().uqs_device_sm_count())
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def replay(p: Params, x, y, yaw_deg, ranges, out: Optional[np.ndarray] = None):
+    """``uqs_replay``: x,y,yaw [F,N], ranges [F,N,32] -> (grids [F,H,W] int8, stats dict)."""
+    x = _f32(x)
+    if x.ndim == 1:
+        x = x[None]
+    F, N = x.shape
+    y, yaw_deg = _f32(y).reshape(F, N), _f32(yaw_deg).reshape(F, N)
+    ranges = _f32(ranges).reshape(F, N, BEAMS_PER_FRAME)
+    grids = out if out is not None else np.empty((F, p.H, p.W), np.int8)
+    st = Stats()
+    _check(lib().uqs_replay(C.byref(p), F, N, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(grids), C.byref(st)))
+    return grids, st.as_dict()
+
+
+def replay_flow(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, ranges, want_poses=True):
+    """``uqs_replay_flow``: P0 then the replay, one frame per flow sample."""
+    t_ms = np.ascontiguousarray(t_ms, dtype=np.uint32)
+    if t_ms.ndim == 1:
+        t_ms = t_ms[None]
+    F, N = t_ms.shape
+    rx, ry, h, yaw = (_f32(a).reshape(F, N) for a in (of_rate_x, of_rate_y, h_m, yaw_deg))
+    q = np.ascontiguousarray(of_q, dtype=np.uint8).reshape(F, N)
+    ranges = _f32(ranges).reshape(F, N, BEAMS_PER_FRAME)
+    grids = np.empty((F, p.H, p.W), np.int8)
+    px = np.empty((F, N), np.float32) if want_poses else None
+    py = np.empty((F, N), np.float32) if want_poses else None
+    st = Stats()
+    _check(lib().uqs_replay_flow(C.byref(p), F, N, _ptr(t_ms), _ptr(rx), _ptr(ry), _ptr(h), _ptr(yaw), _ptr(q),
+                                 _ptr(ranges), _ptr(grids), _ptr(px) if want_poses else None,
+                                 _ptr(py) if want_poses else None, C.byref(st)))
+    return grids, px, py, st.as_dict()
+
+
+def pose_integrate(t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, mode: int = 0):
+    """``uqs_pose_integrate`` (P0, builder-defined): returns x, y [F,N] float32."""
+    t_ms = np.ascontiguousarray(t_ms, dtype=np.uint32)
+    if t_ms.ndim == 1:
+        t_ms = t_ms[None]
+    F, N = t_ms.shape
+    rx, ry, h, yaw = (_f32(a).reshape(F, N) for a in (of_rate_x, of_rate_y, h_m, yaw_deg))
+    q = np.ascontiguousarray(of_q, dtype=np.uint8).reshape(F, N)
+    xo, yo = np.empty((F, N), np.float32), np.empty((F, N), np.float32)
+    _check(lib().uqs_pose_integrate(F, N, _ptr(t_ms), _ptr(rx), _ptr(ry), _ptr(h), _ptr(yaw), _ptr(q), _ptr(xo),
+                                    _ptr(yo), int(mode)))
+    return xo, yo
+
+
+def replay_dev(p: Params, n_flights: int, n_frames: int, x_ptr: int, y_ptr: int, yaw_ptr: int, ranges_ptr: int,
+               grids_ptr: int, accumulate: bool = False, row0: int = 0, rows: Optional[int] = None,
+               want_stats: bool = False):
+    """``uqs_replay_dev`` on raw device pointers (e.g. ``tensor.data_ptr()``); asynchronous unless stats are asked."""
+    st = Stats()
+    _check(lib().uqs_replay_dev(C.byref(p), n_flights, n_frames, C.c_void_p(x_ptr), C.c_void_p(y_ptr),
+                                C.c_void_p(yaw_ptr), C.c_void_p(ranges_ptr), C.c_void_p(grids_ptr),
+                                1 if accumulate else 0, row0, p.H if rows is None else rows,
+                                C.byref(st) if want_stats else None))
+    return st.as_dict() if want_stats else None
+
+
+def pose_integrate_dev(n_flights, n_samples, t_ptr, rx_ptr, ry_ptr, h_ptr, yaw_ptr, q_ptr, xo_ptr, yo_ptr, mode=0):
+    _check(lib().uqs_pose_integrate_dev(n_flights, n_samples, *(C.c_void_p(v) for v in
+                                        (t_ptr, rx_ptr, ry_ptr, h_ptr, yaw_ptr, q_ptr, xo_ptr, yo_ptr)), int(mode)))
+
+
+def beam_cells(p: Params, x, y, yaw_deg, ranges):
+    """End cell of every beam (A3/A6 parity hook): returns cells [N,32,2], origin [N,2] (int32, -1 = dropped)."""
+    x, y, yaw_deg = _f32(x).ravel(), _f32(y).ravel(), _f32(yaw_deg).ravel()
+    N = x.size
+    ranges = _f32(ranges).reshape(N, BEAMS_PER_FRAME)
+    cells = np.empty((N, BEAMS_PER_FRAME, 2), np.int32)
+    origin = np.empty((N, 2), np.int32)
+    _check(lib().uqs_beam_cells(C.byref(p), N, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(cells), _ptr(origin)))
+    return cells, origin
+
+
+def sincosf_batch(ang):
+    ang = _f32(ang).ravel()
+    s, c = np.empty_like(ang), np.empty_like(ang)
+    _check(lib().uqs_sincosf_batch(ang.size, _ptr(ang), _ptr(s), _ptr(c)))
+    return s, c
+
+
+def measure_rmw_peak() -> float:
+    v = C.c_double(0)
+    _check(lib().uqs_measure_rmw_peak(C.byref(v)))
+    return float(v.value)
+
+
+class DropIn:
+    """The reference's own symbols (``map_update_from_beams`` & co.) through the C ABI."""
+
+    def __init__(self, p: Params):
+        self.L = lib()
+        self.p = p.copy()
+        _check(self.L.uqs_dropin_configure(C.byref(self.p)))
+
+    def _g(self, ctype, name):
+        return ctype.in_dll(self.L, name)
+
+    def hover_init(self, ox: float, oy: float):
+        """uav_local_nav.c:2187-2194: origin := pose, clear grid, map_inited = true."""
+        self._g(C.c_float, "map_origin_x").value = ox
+        self._g(C.c_float, "map_origin_y").value = oy
+        self.L.map_reset()
+        self._g(C.c_bool, "map_inited").value = True
+
+    def set_inited(self, v: bool):
+        self._g(C.c_bool, "map_inited").value = v
+
+    def set_beams(self, beams32):
+        arr = (C.c_float * 32).in_dll(self.L, "tof_beams_m")
+        b = _f32(beams32).ravel()
+        C.memmove(arr, b.ctypes.data, 128)
+
+    def map_update_from_beams(self, x, y, yaw):
+        self.L.map_update_from_beams(np.float32(x), np.float32(y), np.float32(yaw))
+
+    def raycast_update(self, x0, y0, x1, y1, hit):
+        self.L.raycast_update(np.float32(x0), np.float32(y0), np.float32(x1), np.float32(y1), bool(hit))
+
+    def world_to_grid(self, x, y):
+        gx, gy = C.c_int(-1), C.c_int(-1)
+        ok = self.L.world_to_grid(np.float32(x), np.float32(y), C.byref(gx), C.byref(gy))
+        return bool(ok), gx.value, gy.value
+
+    def grid(self) -> np.ndarray:
+        self.L.uqs_dropin_flush()
+        ptr = C.POINTER(C.c_int8).in_dll(self.L, "occ_grid")
+        return np.ctypeslib.as_array(ptr, shape=(self.p.H, self.p.W)).copy()

@@ -1,0 +1,565 @@
+// uqs_api.cu -- host side of the C ABI declared in include/uqs_mapping.h (batch symbols).
+//
+// Plain C-callable functions; the library owns its CUDA stream and scratch buffers,
+// callers own every buffer they pass.  No CPU implementation of the path exists in
+// this library: without a usable CUDA device every call returns UQS_ERR_NO_DEVICE /
+// UQS_ERR_NOT_INIT.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/uqs_mapping.h"
+#include "uqs_host.h"
+
+namespace uqs {
+
+Context g_ctx;
+
+static char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return UQS_ERR_CUDA;
+}
+
+int DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return UQS_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) {
+    p = nullptr;
+    set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    return UQS_ERR_NOMEM;
+  }
+  cap = want;
+  return UQS_OK;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+int check_ready() {
+  if (!g_ctx.ready) {
+    if (!g_err[0]) set_error("uqs_init() has not been called or failed");
+    return UQS_ERR_NOT_INIT;
+  }
+  return UQS_OK;
+}
+
+int make_dev_params(const uqs_params* p, DevParams* d) {
+  if (!p) { set_error("params is NULL"); return UQS_ERR_BAD_ARG; }
+  if (p->W < 2 || p->H < 2 || p->W > 32766 || p->H > 32766) {
+    set_error("grid size %dx%d outside [2, 32766]", p->W, p->H);
+    return UQS_ERR_BAD_ARG;
+  }
+  if (!(p->res_m > 0.0f) || !std::isfinite(p->origin_x) || !std::isfinite(p->origin_y)) {
+    set_error("res_m must be > 0 and the origin finite");
+    return UQS_ERR_BAD_ARG;
+  }
+  if (p->lo_min < -128 || p->lo_max > 127 || p->lo_min > p->lo_max) {
+    set_error("log-odds clamp [%d,%d] does not fit int8", p->lo_min, p->lo_max);
+    return UQS_ERR_BAD_ARG;
+  }
+  if (p->lo_free < 0 || p->lo_free > 127 || p->lo_occ < 0 || p->lo_occ > 127) {
+    set_error("log-odds steps must be in [0,127]");
+    return UQS_ERR_BAD_ARG;
+  }
+  d->W = p->W; d->H = p->H; d->halfW = p->W / 2; d->halfH = p->H / 2;
+  d->res = p->res_m; d->ox = p->origin_x; d->oy = p->origin_y;
+  d->max_range = p->max_range_m; d->min_range = p->min_range_m;
+  // the same binary32 operations the reference's compiler folds (uav_local_nav.c:284,292,299)
+  volatile float mr = p->max_range_m, hm = p->hit_margin_m, fov = p->fov_deg;
+  volatile float pi_f = (float)M_PI;
+  d->hit_below = mr - hm;
+  d->half_fov = fov * 0.5f;
+  d->deg2rad = pi_f / 180.0f;
+  d->lo_free = p->lo_free; d->lo_occ = p->lo_occ; d->lo_min = p->lo_min; d->lo_max = p->lo_max;
+  d->end_nohit = -(p->lo_free / 2);
+  return UQS_OK;
+}
+
+// sub-tile geometry for a grid of W columns and `rows` owned rows
+static void choose_tiles(int W, int rows, int* sw, int* sh, int* nsx, int* nsy) {
+  auto pick = [](int extent, int forced, int* size, int* count) {
+    if (forced > 0) {
+      *size = std::min(forced, extent);
+    } else {
+      int n = std::max(1, (extent + 40) / 80);        // aim at ~80-cell sub-tiles
+      int s = (extent + n - 1) / n;
+      s = (s + 3) & ~3;
+      *size = std::min(s, extent);
+    }
+    *count = (extent + *size - 1) / *size;
+  };
+  pick(W, g_ctx.tune_sw, sw, nsx);
+  pick(rows, g_ctx.tune_sh, sh, nsy);
+}
+
+int replay_device(const DevParams& dp, int n_flights, int n_frames, const float* x, const float* y,
+                  const float* yaw, const float* ranges, const uint8_t* kind, int8_t* grids,
+                  int accumulate, int row0, int rows, bool reset_stats) {
+  cudaStream_t st = g_ctx.stream();
+  const int gpf = (n_frames + 31) / 32;
+  int sw, sh, nsx, nsy;
+  choose_tiles(dp.W, rows, &sw, &sh, &nsx, &nsy);
+  int pitch = (sw + 3) & ~3;
+  if (((pitch >> 2) & 1) == 0) pitch += 4;            // odd word pitch: column walks hit 32 banks
+  const int tile_bytes = pitch * sh;
+  const size_t smem = (size_t)tile_bytes * kReplayWarps;
+  if (smem > 227u * 1024u) {
+    set_error("sub-tile %dx%d needs %zu B of shared memory per CTA (> 227 KB)", sw, sh, smem);
+    return UQS_ERR_BAD_ARG;
+  }
+
+  // scratch is bounded: flights are processed in chunks of at most `chunk` flights
+  const size_t per_flight = (size_t)n_frames * (32 * sizeof(uint2) + sizeof(uint4)) + (size_t)gpf * sizeof(uint2);
+  const size_t budget = g_ctx.scratch_budget;
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_flights, budget / std::max<size_t>(per_flight, 1)));
+  int rc;
+  if ((rc = g_ctx.ws_rays.ensure((size_t)chunk * n_frames * 32 * sizeof(uint2)))) return rc;
+  if ((rc = g_ctx.ws_frames.ensure((size_t)chunk * n_frames * sizeof(uint4)))) return rc;
+  if ((rc = g_ctx.ws_groups.ensure((size_t)chunk * gpf * sizeof(uint2)))) return rc;
+  if ((rc = g_ctx.ws_counters.ensure(64 * sizeof(unsigned long long)))) return rc;
+  unsigned long long* counters = (unsigned long long*)g_ctx.ws_counters.p;   // [0..3] stats, [8+] job counters
+  cudaError_t e;
+  if (reset_stats) {
+    e = cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset stats");
+  }
+
+  e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_replay_tiles, kReplayThreads, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "occupancy(k_replay_tiles)");
+  if (ctas_per_sm < 1) { set_error("k_replay_tiles does not fit on an SM (smem %zu)", smem); return UQS_ERR_CUDA; }
+
+  for (int f0 = 0; f0 < n_flights; f0 += chunk) {
+    const int nf = std::min(chunk, n_flights - f0);
+    const size_t fo = (size_t)f0 * n_frames;
+    k_ray_setup<<<(unsigned)(nf * gpf), 1024, 0, st>>>(
+        dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr,
+        (uint4*)g_ctx.ws_frames.p, (uint2*)g_ctx.ws_groups.p, (uint2*)g_ctx.ws_rays.p, counters);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_ray_setup launch");
+
+    ReplayArgs A;
+    A.frames = (const uint4*)g_ctx.ws_frames.p;
+    A.groups = (const uint2*)g_ctx.ws_groups.p;
+    A.rays = (const uint2*)g_ctx.ws_rays.p;
+    A.grids = grids + (size_t)f0 * dp.W * dp.H;
+    A.job_counter = counters + 8;
+    A.total_jobs = (unsigned long long)nf * nsx * nsy;
+    A.n_frames = n_frames; A.groups_per_flight = gpf;
+    A.W = dp.W; A.H = dp.H; A.row0 = row0; A.rows = rows;
+    A.sw = sw; A.sh = sh; A.nsx = nsx; A.nsy = nsy;
+    A.pitch = pitch; A.tile_bytes = tile_bytes;
+    A.lo_free = dp.lo_free; A.lo_occ = dp.lo_occ; A.lo_min = dp.lo_min; A.lo_max = dp.lo_max;
+    A.end_nohit = dp.end_nohit;
+    A.accumulate = accumulate;
+    e = cudaMemsetAsync(A.job_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset job counter");
+    unsigned long long want = (A.total_jobs + kReplayWarps - 1) / kReplayWarps;
+    unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctas_per_sm * g_ctx.sm_count);
+    k_replay_tiles<<<grid, kReplayThreads, smem, st>>>(A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_replay_tiles launch");
+    g_ctx.launches += 2;
+  }
+  return UQS_OK;
+}
+
+int fetch_stats(uqs_stats* stats, uint64_t frames) {
+  if (!stats) return UQS_OK;
+  unsigned long long h[4];
+  cudaError_t e = cudaMemcpyAsync(h, g_ctx.ws_counters.p, sizeof(h), cudaMemcpyDeviceToHost, g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, "stats D2H");
+  e = cudaStreamSynchronize(g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, "stats sync");
+  stats->ray_cell_updates = h[0];
+  stats->rays_accepted = h[1];
+  stats->rays_skipped = h[2];
+  stats->domain_errors = h[3];
+  stats->frames = frames;
+  if (h[3]) {
+    set_error("%llu rays left the exact-arithmetic domain (|angle| >= 120 rad or > %d cells)", h[3], kMaxRayCells);
+    return UQS_ERR_DOMAIN;
+  }
+  return UQS_OK;
+}
+
+int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float* rx, const float* ry,
+                const float* h, const float* yaw, const uint8_t* q, float* xo, float* yo, int mode) {
+  cudaStream_t st = g_ctx.stream();
+  const long long total = (long long)n_flights * n_samples;
+  int rc;
+  if ((rc = g_ctx.ws_inc.ensure((size_t)total * 2 * sizeof(float)))) return rc;
+  if ((rc = g_ctx.ws_counters.ensure(64 * sizeof(unsigned long long)))) return rc;
+  float* inc_n = (float*)g_ctx.ws_inc.p;
+  float* inc_e = inc_n + total;
+  unsigned long long* dom = (unsigned long long*)g_ctx.ws_counters.p + 16;
+  cudaError_t e = cudaMemsetAsync(dom, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset pose counter");
+  volatile float pi_f = (float)M_PI;
+  const float deg2rad = pi_f / 180.0f;
+  k_pose_increments<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, n_samples, t_ms, rx, ry, h, yaw, q,
+                                                                     deg2rad, inc_n, inc_e, dom);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_pose_increments launch");
+  if (mode == 0) {
+    const int warps_per_block = 4;
+    k_pose_chain<<<(unsigned)((n_flights + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
+        n_flights, n_samples, inc_n, inc_e, xo, yo);
+  } else {
+    const int tile = pose_scan_tile();
+    const int ppf = (n_samples + tile - 1) / tile;
+    const size_t nparts = (size_t)n_flights * ppf;
+    if ((rc = g_ctx.ws_scan.ensure(nparts * pose_scan_state_bytes() + 64))) return rc;
+    e = cudaMemsetAsync(g_ctx.ws_scan.p, 0, nparts * pose_scan_state_bytes() + 64, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset scan state");
+    unsigned int* ticket = (unsigned int*)((char*)g_ctx.ws_scan.p + nparts * pose_scan_state_bytes());
+    k_pose_scan<<<(unsigned)nparts, pose_scan_threads(), 0, st>>>(n_flights, n_samples, ppf, inc_n, inc_e, xo, yo,
+                                                                  (volatile ScanState*)g_ctx.ws_scan.p, ticket);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pose kernel launch");
+  g_ctx.launches += 2;
+  return UQS_OK;
+}
+
+}  // namespace uqs
+
+using namespace uqs;
+
+extern "C" {
+
+void uqs_params_default(uqs_params* p) {
+  if (!p) return;
+  p->W = 500; p->H = 500; p->res_m = 0.10f; p->size_m = 50.0f;      /* uav_local_nav.c:182-186 */
+  p->origin_x = 0.0f; p->origin_y = 0.0f;
+  p->max_range_m = 4.00f; p->fov_deg = 63.0f;                        /* :117-118 */
+  p->min_range_m = 0.05f; p->hit_margin_m = 0.05f;                   /* :290, :292 */
+  p->lo_free = 1; p->lo_occ = 6; p->lo_min = -80; p->lo_max = 80;    /* :194-197 */
+}
+
+const char* uqs_last_error(void) { return g_err; }
+
+int uqs_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    g_ctx.ready = false;
+    return UQS_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return UQS_ERR_BAD_ARG; }
+  if (g_ctx.ready && g_ctx.device == device) return UQS_OK;
+  if (g_ctx.ready) uqs_shutdown();
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return UQS_ERR_NO_DEVICE;
+  }
+  if ((e = cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return cuda_fail(e, "cudaStreamCreate");
+  g_ctx.device = device;
+  g_ctx.sm_count = prop.multiProcessorCount;
+  g_ctx.ext_stream = nullptr;
+  g_ctx.use_ext = false;
+  g_ctx.ready = true;
+  g_err[0] = 0;
+  return UQS_OK;
+}
+
+void uqs_shutdown(void) {
+  if (!g_ctx.ready) return;
+  cudaSetDevice(g_ctx.device);
+  cudaDeviceSynchronize();
+  dropin_release();
+  g_ctx.release_all();
+  if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+  g_ctx.own_stream = nullptr;
+  g_ctx.ready = false;
+}
+
+int uqs_device_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
+
+int uqs_set_stream(void* s) {
+  int rc = check_ready();
+  if (rc) return rc;
+  g_ctx.ext_stream = (cudaStream_t)s;
+  g_ctx.use_ext = true;      /* NULL = the legacy default stream, which torch uses unless told otherwise */
+  return UQS_OK;
+}
+
+int uqs_use_own_stream(void) {
+  int rc = check_ready();
+  if (rc) return rc;
+  g_ctx.use_ext = false;
+  return UQS_OK;
+}
+
+int uqs_sync(void) {
+  int rc = check_ready();
+  if (rc) return rc;
+  cudaError_t e = cudaStreamSynchronize(g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return UQS_OK;
+}
+
+int uqs_set_tuning(int sw, int sh, int time_slices) {
+  if (sw < 0 || sh < 0 || time_slices < 0) { set_error("negative tuning value"); return UQS_ERR_BAD_ARG; }
+  g_ctx.tune_sw = sw;
+  g_ctx.tune_sh = sh;
+  g_ctx.tune_slices = time_slices;
+  return UQS_OK;
+}
+
+unsigned long long uqs_kernel_launches(void) { return g_ctx.launches; }
+
+int uqs_replay_dev(const uqs_params* p, int n_flights, int n_frames, const float* x, const float* y,
+                   const float* yaw, const float* ranges, int8_t* grids, int accumulate, int row0,
+                   int rows, uqs_stats* stats) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_flights <= 0 || n_frames <= 0 || !x || !y || !yaw || !ranges || !grids) {
+    set_error("uqs_replay_dev: NULL pointer or non-positive size");
+    return UQS_ERR_BAD_ARG;
+  }
+  if (row0 < 0 || rows <= 0 || row0 + rows > p->H) { set_error("row range [%d,%d) outside the grid", row0, row0 + rows); return UQS_ERR_BAD_ARG; }
+  if ((rc = replay_device(dp, n_flights, n_frames, x, y, yaw, ranges, nullptr, grids, accumulate, row0, rows, true)))
+    return rc;
+  return fetch_stats(stats, (uint64_t)n_flights * n_frames);
+}
+
+int uqs_pose_integrate_dev(int n_flights, int n_samples, const uint32_t* t_ms, const float* rx,
+                           const float* ry, const float* h, const float* yaw, const uint8_t* q,
+                           float* xo, float* yo, int mode) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n_flights <= 0 || n_samples <= 0 || !t_ms || !rx || !ry || !h || !yaw || !q || !xo || !yo || (mode != 0 && mode != 1)) {
+    set_error("uqs_pose_integrate_dev: bad argument");
+    return UQS_ERR_BAD_ARG;
+  }
+  return pose_device(n_flights, n_samples, t_ms, rx, ry, h, yaw, q, xo, yo, mode);
+}
+
+/* ---- host-buffer forms: stage through library-owned device buffers --------------------- */
+
+static int h2d(DevBuf& b, const void* src, size_t bytes, const char* what) {
+  int rc = b.ensure(bytes);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  return UQS_OK;
+}
+
+int uqs_pose_integrate(int n_flights, int n_samples, const uint32_t* t_ms, const float* rx,
+                       const float* ry, const float* h, const float* yaw, const uint8_t* q,
+                       float* xo, float* yo, int mode) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n_flights <= 0 || n_samples <= 0 || !t_ms || !rx || !ry || !h || !yaw || !q || !xo || !yo || (mode != 0 && mode != 1)) {
+    set_error("uqs_pose_integrate: bad argument");
+    return UQS_ERR_BAD_ARG;
+  }
+  const size_t n = (size_t)n_flights * n_samples;
+  if ((rc = h2d(g_ctx.in_t, t_ms, n * 4, "t_ms H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_rx, rx, n * 4, "of_rate_x H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_ry, ry, n * 4, "of_rate_y H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_h, h, n * 4, "h_m H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_q, q, n, "of_q H2D"))) return rc;
+  if ((rc = g_ctx.in_x.ensure(n * 4)) || (rc = g_ctx.in_y.ensure(n * 4))) return rc;
+  if ((rc = pose_device(n_flights, n_samples, (uint32_t*)g_ctx.in_t.p, (float*)g_ctx.in_rx.p, (float*)g_ctx.in_ry.p,
+                        (float*)g_ctx.in_h.p, (float*)g_ctx.in_yaw.p, (uint8_t*)g_ctx.in_q.p, (float*)g_ctx.in_x.p,
+                        (float*)g_ctx.in_y.p, mode)))
+    return rc;
+  cudaError_t e = cudaMemcpyAsync(xo, g_ctx.in_x.p, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream());
+  if (e == cudaSuccess) e = cudaMemcpyAsync(yo, g_ctx.in_y.p, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream());
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, "pose D2H");
+  return UQS_OK;
+}
+
+static int replay_host_common(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames,
+                              const float* ranges, int8_t* grids_out, uqs_stats* stats) {
+  int rc;
+  const size_t n = (size_t)n_flights * n_frames;
+  const size_t gbytes = (size_t)n_flights * p->W * p->H;
+  if ((rc = h2d(g_ctx.in_ranges, ranges, n * 32 * 4, "ranges H2D"))) return rc;
+  if ((rc = g_ctx.out_grids.ensure(gbytes))) return rc;
+  if ((rc = replay_device(dp, n_flights, n_frames, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p, (float*)g_ctx.in_yaw.p,
+                          (float*)g_ctx.in_ranges.p, nullptr, (int8_t*)g_ctx.out_grids.p, 0, 0, p->H, true)))
+    return rc;
+  cudaError_t e = cudaMemcpyAsync(grids_out, g_ctx.out_grids.p, gbytes, cudaMemcpyDeviceToHost, g_ctx.stream());
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, "grids D2H");
+  uqs_stats local;
+  rc = fetch_stats(stats ? stats : &local, n);
+  return rc;
+}
+
+int uqs_replay(const uqs_params* p, int n_flights, int n_frames, const float* x, const float* y,
+               const float* yaw, const float* ranges, int8_t* grids_out, uqs_stats* stats) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_flights <= 0 || n_frames <= 0 || !x || !y || !yaw || !ranges || !grids_out) {
+    set_error("uqs_replay: NULL pointer or non-positive size");
+    return UQS_ERR_BAD_ARG;
+  }
+  const size_t n = (size_t)n_flights * n_frames;
+  if ((rc = h2d(g_ctx.in_x, x, n * 4, "x H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_y, y, n * 4, "y H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D"))) return rc;
+  return replay_host_common(p, dp, n_flights, n_frames, ranges, grids_out, stats);
+}
+
+int uqs_replay_flow(const uqs_params* p, int n_flights, int n_samples, const uint32_t* t_ms,
+                    const float* rx, const float* ry, const float* h, const float* yaw,
+                    const uint8_t* q, const float* ranges, int8_t* grids_out, float* pox, float* poy,
+                    uqs_stats* stats) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_flights <= 0 || n_samples <= 0 || !t_ms || !rx || !ry || !h || !yaw || !q || !ranges || !grids_out) {
+    set_error("uqs_replay_flow: NULL pointer or non-positive size");
+    return UQS_ERR_BAD_ARG;
+  }
+  const size_t n = (size_t)n_flights * n_samples;
+  if ((rc = h2d(g_ctx.in_t, t_ms, n * 4, "t_ms H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_rx, rx, n * 4, "of_rate_x H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_ry, ry, n * 4, "of_rate_y H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_h, h, n * 4, "h_m H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D"))) return rc;
+  if ((rc = h2d(g_ctx.in_q, q, n, "of_q H2D"))) return rc;
+  if ((rc = g_ctx.in_x.ensure(n * 4)) || (rc = g_ctx.in_y.ensure(n * 4))) return rc;
+  if ((rc = pose_device(n_flights, n_samples, (uint32_t*)g_ctx.in_t.p, (float*)g_ctx.in_rx.p, (float*)g_ctx.in_ry.p,
+                        (float*)g_ctx.in_h.p, (float*)g_ctx.in_yaw.p, (uint8_t*)g_ctx.in_q.p, (float*)g_ctx.in_x.p,
+                        (float*)g_ctx.in_y.p, 0)))
+    return rc;
+  if (pox && poy) {
+    cudaError_t e = cudaMemcpyAsync(pox, g_ctx.in_x.p, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(poy, g_ctx.in_y.p, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream());
+    if (e != cudaSuccess) return cuda_fail(e, "pose D2H");
+  }
+  return replay_host_common(p, dp, n_flights, n_samples, ranges, grids_out, stats);
+}
+
+int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const float* y, const float* yaw,
+                   const float* ranges, int32_t* cells_out, int32_t* origin_out) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_frames <= 0 || !x || !y || !yaw || !ranges || !cells_out || !origin_out) { set_error("uqs_beam_cells: bad argument"); return UQS_ERR_BAD_ARG; }
+  cudaStream_t st = g_ctx.stream();
+  const size_t n = (size_t)n_frames;
+  const int gpf = (n_frames + 31) / 32;
+  if ((rc = h2d(g_ctx.in_x, x, n * 4, "x H2D")) || (rc = h2d(g_ctx.in_y, y, n * 4, "y H2D")) ||
+      (rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D")) || (rc = h2d(g_ctx.in_ranges, ranges, n * 128, "ranges H2D")))
+    return rc;
+  if ((rc = g_ctx.ws_rays.ensure(n * 32 * sizeof(uint2))) || (rc = g_ctx.ws_frames.ensure(n * sizeof(uint4))) ||
+      (rc = g_ctx.ws_groups.ensure((size_t)gpf * sizeof(uint2))) || (rc = g_ctx.ws_counters.ensure(64 * 8)) ||
+      (rc = g_ctx.out_grids.ensure(n * 32 * 2 * 4 + n * 2 * 4)))
+    return rc;
+  cudaError_t e = cudaMemsetAsync(g_ctx.ws_counters.p, 0, 64, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset");
+  k_ray_setup<<<(unsigned)gpf, 1024, 0, st>>>(dp, n_frames, gpf, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p,
+                                              (float*)g_ctx.in_yaw.p, (float*)g_ctx.in_ranges.p, nullptr,
+                                              (uint4*)g_ctx.ws_frames.p, (uint2*)g_ctx.ws_groups.p,
+                                              (uint2*)g_ctx.ws_rays.p, (unsigned long long*)g_ctx.ws_counters.p);
+  int32_t* d_cells = (int32_t*)g_ctx.out_grids.p;
+  int32_t* d_origin = d_cells + n * 64;
+  k_records_to_cells<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>((long long)n, (uint4*)g_ctx.ws_frames.p,
+                                                                       (uint2*)g_ctx.ws_rays.p, d_cells, d_origin);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "beam_cells kernels");
+  e = cudaMemcpyAsync(cells_out, d_cells, n * 64 * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(origin_out, d_origin, n * 2 * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "beam_cells D2H");
+  g_ctx.launches += 2;
+  return UQS_OK;
+}
+
+int uqs_sincosf_batch(size_t n, const float* ang, float* s, float* c) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (!n || !ang || !s || !c) { set_error("uqs_sincosf_batch: bad argument"); return UQS_ERR_BAD_ARG; }
+  cudaStream_t st = g_ctx.stream();
+  if ((rc = h2d(g_ctx.in_x, ang, n * 4, "ang H2D")) || (rc = g_ctx.in_y.ensure(n * 4)) || (rc = g_ctx.in_yaw.ensure(n * 4)))
+    return rc;
+  k_sincosf<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p, (float*)g_ctx.in_yaw.p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s, g_ctx.in_y.p, n * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c, g_ctx.in_yaw.p, n * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "sincosf batch");
+  g_ctx.launches += 1;
+  return UQS_OK;
+}
+
+int uqs_measure_rmw_peak(double* updates_per_s) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (!updates_per_s) { set_error("NULL output"); return UQS_ERR_BAD_ARG; }
+  cudaStream_t st = g_ctx.stream();
+  const int tile_bytes = 6400, iters = 4096;
+  const size_t smem = (size_t)tile_bytes * kReplayWarps;
+  cudaError_t e = cudaFuncSetAttribute(k_rmw_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_rmw_peak)");
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rmw_peak, kReplayThreads, smem);
+  if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "occupancy(k_rmw_peak)");
+  if ((rc = g_ctx.ws_counters.ensure(64 * 8))) return rc;
+  const unsigned grid = (unsigned)(per_sm * g_ctx.sm_count);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  k_rmw_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, 64, -80, (int*)g_ctx.ws_counters.p + 96);
+  cudaEventRecord(a, st);
+  k_rmw_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, iters, -80, (int*)g_ctx.ws_counters.p + 96);
+  cudaEventRecord(b, st);
+  e = cudaEventSynchronize(b);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (e != cudaSuccess) return cuda_fail(e, "k_rmw_peak");
+  const double updates = (double)grid * kReplayThreads * (double)iters * 8.0;
+  *updates_per_s = updates / (ms * 1e-3);
+  g_ctx.launches += 2;
+  return UQS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// uqs_device.cuh -- exact device arithmetic of the mapping path (sm_100a).
+//
+// Every float operation below is an explicit round-to-nearest intrinsic
+// (__fadd_rn/__fmul_rn/__fdiv_rn never contract into FMA), mirroring one C
+// operator of the reference each, in source order.  The
+// translation unit is additionally compiled with -fmad=false.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace uqs {
+
+// Device copy of uqs_params plus the constants the reference folds at compile time.
+struct DevParams {
+  int   W, H, halfW, halfH;
+  float res, ox, oy;
+  float max_range, min_range, hit_below;  // hit_below = max_range - hit_margin (uav_local_nav.c:292)
+  float half_fov;                         // fov * 0.5f                          (:284)
+  float deg2rad;                          // (float)M_PI / 180.0f                (:299)
+  int   lo_free, lo_occ, lo_min, lo_max;
+  int   end_nohit;                        // -(lo_free / 2), integer division   (:266)
+};
+
+// Ray record, 8 bytes:  w0 = dx[12 signed] | dy[12 signed]<<12 | hit<<24 | valid<<25
+//                       w1 = ceil(2^31 / m), m = max(|dx|,|dy|)  (0 when m == 0)
+// Frame record, 16 bytes: x = origin cell gx, y = gy (or -1,-1),
+//                         z = xmin | xmax<<16, w = ymin | ymax<<16  (bbox of all cells the
+//                         frame's accepted rays touch; empty bbox = min 0x7fff, max 0)
+constexpr int      kMaxRayCells   = 1024;       // magic-division exactness bound
+constexpr uint32_t kRayHit        = 1u << 24;
+constexpr uint32_t kRayValid      = 1u << 25;
+constexpr uint32_t kEmptyBoxLoHi  = 0x00007fffu;  // min = 0x7fff, max = 0  -> never overlaps
+
+// ---------------------------------------------------------------------------
+// glibc 2.39 sincosf, FMA build, restated.  Returns false
+// when |y| >= 120 or y is not finite: that branch (reduce_large) is not restated,
+// the caller must drop the ray and raise UQS_ERR_DOMAIN.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool sincosf_glibc(float y, float& sn, float& cs) {
+  const uint32_t top12 = (__float_as_uint(y) >> 20) & 0x7ffu;
+  double x = (double)y;
+  double xs = x;
+  int n = 0;
+  if (top12 < 0x3f4u) {                       // |y| < pi/4
+    if (top12 < 0x398u) {                     // |y| < 2^-12
+      sn = y;
+      cs = 1.0f;
+      return true;
+    }
+  } else if (top12 < 0x42fu) {                // |y| < 120
+    const double r = __dmul_rn(x, 0x1.45f306dc9c883p+23);
+    n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __fma_rn(-(double)n, 0x1.921fb54442d18p+0, x);
+    xs = ((n + 1) & 2) ? -x : x;              // sign table {+,-,-,+}[n & 3]
+  } else {
+    sn = cs = __int_as_float(0x7fc00000);
+    return false;
+  }
+  const double x2 = __dmul_rn(x, x);
+  const double x3 = __dmul_rn(x2, xs);
+  const double x4 = __dmul_rn(x2, x2);
+  const double s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+  const double c2 = __fma_rn(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
+  const double c1 = __fma_rn(x2, -0x1.ffffffd0c621cp-2, 1.0);
+  const double x5 = __dmul_rn(x2, x3);
+  const double x6 = __dmul_rn(x2, x4);
+  double S = __fma_rn(x3, -0x1.555545995a603p-3, xs);
+  double C = __fma_rn(x4, 0x1.55553e1068f19p-5, c1);
+  S = __fma_rn(x5, s1, S);
+  C = __fma_rn(x6, c2, C);
+  if (n & 2) C = -C;                          // second table = cosine coefficients negated
+  const float fs = __double2float_rn(S), fc = __double2float_rn(C);
+  if (n & 1) { cs = fs; sn = fc; } else { sn = fs; cs = fc; }
+  return true;
+}
+
+// (int)lrintf(q): x86-64 cvtss2si yields 0x8000000000000000 for NaN and |q| >= 2^63,
+// whose low 32 bits are 0; in range the cast keeps the low 32 bits.
+__device__ __forceinline__ int lrintf_as_int(float q) {
+  const long long r = (fabsf(q) < 9223372036854775808.0f) ? __float2ll_rn(q)
+                                                          : (long long)0x8000000000000000ull;
+  return (int)r;
+}
+
+// world_to_grid(), uav_local_nav.c:205-214
+__device__ __forceinline__ bool world_to_grid(const DevParams& p, float wx, float wy, int& gx,
+                                              int& gy) {
+  const float ddx = __fsub_rn(wx, p.ox);
+  const float ddy = __fsub_rn(wy, p.oy);
+  const int ix = (int)((unsigned)lrintf_as_int(__fdiv_rn(ddx, p.res)) + (unsigned)p.halfW);
+  const int iy = (int)((unsigned)lrintf_as_int(__fdiv_rn(ddy, p.res)) + (unsigned)p.halfH);
+  gx = ix;
+  gy = iy;
+  return !(ix < 0 || ix >= p.W || iy < 0 || iy >= p.H);
+}
+
+// Beam b of map_update_from_beams(), uav_local_nav.c:286-303, up to the end point.
+//   returns 0: skipped (:289-290), 1: end point computed, -1: angle outside the restated domain
+__device__ __forceinline__ int beam_endpoint(const DevParams& p, float px, float py, float yaw_deg,
+                                             float dist, int b, float& ex, float& ey, bool& hit) {
+  if (isnan(dist)) return 0;
+  if (dist <= p.min_range) return 0;
+  hit = dist < p.hit_below;
+  if (dist > p.max_range) dist = p.max_range;
+  const int d = b >> 3, c = b & 7;
+  const float centre = (d == 0) ? 0.0f : (d == 1) ? 90.0f : (d == 2) ? 180.0f : -90.0f;
+  const float u = __fdiv_rn(__fsub_rn((float)c, 3.5f), 3.5f);
+  const float off = __fmul_rn(u, p.half_fov);
+  const float ang_deg = __fadd_rn(__fadd_rn(yaw_deg, centre), off);
+  const float ang = __fmul_rn(ang_deg, p.deg2rad);
+  float sn, cs;
+  if (!sincosf_glibc(ang, sn, cs)) return -1;
+  ex = __fadd_rn(px, __fmul_rn(dist, cs));
+  ey = __fadd_rn(py, __fmul_rn(dist, sn));
+  return 1;
+}
+
+__device__ __forceinline__ int sext12(uint32_t v) { return ((int)(v << 20)) >> 20; }
+
+// q(k) = floor((k*n + m/2) / m) without a divide: n2 = 2n, h2 = 2*(m>>1), inv = ceil(2^31/m).
+// Exact for m <= 1289 (t*m < 2^31 with t <= m*m + m/2); m is capped at kMaxRayCells.
+__device__ __forceinline__ int minor_steps(int k, int n2, int h2, uint32_t inv) {
+  return (int)__umulhi((uint32_t)(k * n2 + h2), inv);
+}
+
+}  // namespace uqs

@@ -1,0 +1,519 @@
+// uqs_kernels.cu -- the CUDA kernels of the mapping path (sm_100a).
+//
+//   k_pose_increments / k_pose_chain / k_pose_scan   P0  (builder-defined)
+//   k_ray_setup        map_update_from_beams() up to the two world_to_grid() calls
+//                      (uav_local_nav.c:280-303, :243-244): one thread per beam, one
+//                      warp per frame, one 1024-thread CTA per group of 32 frames
+//   k_replay_tiles     raycast_update()'s cell loop (uav_local_nav.c:246-277) for whole
+//                      logs: persistent warps, each OWNING a sub-tile of one grid in
+//                      shared memory and applying, in reference order, exactly the
+//                      cell updates that fall inside it
+//
+// Exactness: the reference clamps after every single update, so
+// updates to one cell do not commute.  k_replay_tiles never reorders them: a cell
+// has exactly one owner warp, that warp walks frames in log order and beams in
+// (d,c) order, and the cells of one ray are distinct, so the 32 lanes of the warp
+// can apply one ray's cells at once with plain byte read-modify-writes -- no
+// atomics, no races, bit-identical to the sequential loop.
+#include "uqs_kernels.cuh"
+
+namespace uqs {
+
+// ===========================================================================
+// P0: dead reckoning
+// ===========================================================================
+
+// increment of sample i (i >= 1); sample 0 has increment 0.  All binary32, RN, no contraction.
+__global__ void k_pose_increments(long long total, int n_samples, const uint32_t* __restrict__ t_ms,
+                                  const float* __restrict__ rate_x, const float* __restrict__ rate_y,
+                                  const float* __restrict__ h_m, const float* __restrict__ yaw_deg,
+                                  const uint8_t* __restrict__ q, float deg2rad,
+                                  float* __restrict__ inc_n, float* __restrict__ inc_e,
+                                  unsigned long long* __restrict__ domain_errors) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int s = (int)(i % n_samples);
+  float dn = 0.0f, de = 0.0f;
+  if (s > 0) {
+    const float rx = rate_x[i], ry = rate_y[i], h = h_m[i], yw = yaw_deg[i];
+    if (q[i] >= 50 && !isnan(rx) && !isnan(ry) && !isnan(h) && !isnan(yw)) {
+      const float dt = __fmul_rn((float)(t_ms[i] - t_ms[i - 1]), 0.001f);
+      const float vbx = __fmul_rn(rx, h);
+      const float vby = __fmul_rn(ry, h);
+      const float a = __fmul_rn(yw, deg2rad);
+      float sn, cs;
+      if (sincosf_glibc(a, sn, cs)) {
+        const float vn = __fsub_rn(__fmul_rn(vbx, cs), __fmul_rn(vby, sn));
+        const float ve = __fadd_rn(__fmul_rn(vbx, sn), __fmul_rn(vby, cs));
+        dn = __fmul_rn(vn, dt);
+        de = __fmul_rn(ve, dt);
+      } else {
+        atomicAdd(domain_errors, 1ull);
+      }
+    }
+  }
+  inc_n[i] = dn;
+  inc_e[i] = de;
+}
+
+// One warp per flight replays the summation in sample order.  Lanes load 32 increments
+// at a time (coalesced); the running sum is carried through a shuffle broadcast so every
+// add happens in exactly the order of the CPU statement.
+__global__ void k_pose_chain(int n_flights, int n_samples, const float* __restrict__ inc_n,
+                             const float* __restrict__ inc_e, float* __restrict__ xo,
+                             float* __restrict__ yo) {
+  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_flights) return;
+  const size_t base = (size_t)warp * n_samples;
+  float px = 0.0f, py = 0.0f;
+  for (int s0 = 0; s0 < n_samples; s0 += 32) {
+    const int s = s0 + lane;
+    const float dn = (s < n_samples) ? inc_n[base + s] : 0.0f;
+    const float de = (s < n_samples) ? inc_e[base + s] : 0.0f;
+    float mx = 0.0f, my = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      px = __fadd_rn(px, __shfl_sync(0xffffffffu, dn, j));
+      py = __fadd_rn(py, __shfl_sync(0xffffffffu, de, j));
+      if (j == lane) { mx = px; my = py; }
+    }
+    if (s < n_samples) {
+      xo[base + s] = mx;
+      yo[base + s] = my;
+    }
+  }
+}
+
+// Throughput variant: single-pass chained scan with decoupled look-back, binary64
+// accumulation, one partition of kScanTile samples per CTA.  state[] per partition:
+// flag (0 none, 1 aggregate, 2 inclusive prefix) + two doubles, published with
+// __threadfence().  Partitions are claimed through an atomic ticket so that a
+// partition's predecessors are always already running.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct ScanState { double agg_n, agg_e, inc_n, inc_e; int flag; int pad; };
+
+__global__ void __launch_bounds__(kScanThreads)
+k_pose_scan(int n_flights, int n_samples, int parts_per_flight, const float* __restrict__ inc_n,
+            const float* __restrict__ inc_e, float* __restrict__ xo, float* __restrict__ yo,
+            volatile ScanState* state, unsigned int* ticket) {
+  __shared__ unsigned int s_part;
+  __shared__ double s_wn[kScanThreads / 32], s_we[kScanThreads / 32];
+  __shared__ double s_prefix_n, s_prefix_e;
+  if (threadIdx.x == 0) s_part = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned int part = s_part;
+  if (part >= (unsigned)(n_flights * parts_per_flight)) return;
+  const int flight = part / parts_per_flight, pf = part % parts_per_flight;
+  const size_t base = (size_t)flight * n_samples;
+  const int s_begin = pf * kScanTile + threadIdx.x * kScanItems;
+
+  double vn[kScanItems], ve[kScanItems];
+  double tn = 0.0, te = 0.0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    const int s = s_begin + k;
+    const double a = (s < n_samples) ? (double)inc_n[base + s] : 0.0;
+    const double b = (s < n_samples) ? (double)inc_e[base + s] : 0.0;
+    tn += a; te += b;
+    vn[k] = tn; ve[k] = te;
+  }
+  // warp inclusive scan of thread totals
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double wn = tn, we = te;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double un = __shfl_up_sync(0xffffffffu, wn, o), ue = __shfl_up_sync(0xffffffffu, we, o);
+    if (lane >= o) { wn += un; we += ue; }
+  }
+  if (lane == 31) { s_wn[wid] = wn; s_we[wid] = we; }
+  __syncthreads();
+  double off_n = 0.0, off_e = 0.0;
+  for (int w = 0; w < wid; w++) { off_n += s_wn[w]; off_e += s_we[w]; }
+  const double excl_n = off_n + wn - tn, excl_e = off_e + we - te;   // exclusive thread prefix in tile
+
+  if (threadIdx.x == kScanThreads - 1) {
+    const double agg_n = off_n + wn, agg_e = off_e + we;
+    double pre_n = 0.0, pre_e = 0.0;
+    if (pf == 0) {
+      state[part].inc_n = agg_n; state[part].inc_e = agg_e;
+      __threadfence();
+      state[part].flag = 2;
+    } else {
+      state[part].agg_n = agg_n; state[part].agg_e = agg_e;
+      __threadfence();
+      state[part].flag = 1;
+      // look back over predecessors of the same flight
+      int p = (int)part - 1;
+      for (;;) {
+        int f;
+        while ((f = state[p].flag) == 0) { }
+        __threadfence();
+        if (f == 2) { pre_n += state[p].inc_n; pre_e += state[p].inc_e; break; }
+        pre_n += state[p].agg_n; pre_e += state[p].agg_e;
+        p--;
+      }
+      state[part].inc_n = pre_n + agg_n; state[part].inc_e = pre_e + agg_e;
+      __threadfence();
+      state[part].flag = 2;
+    }
+    s_prefix_n = pre_n; s_prefix_e = pre_e;
+  }
+  __syncthreads();
+  const double bn = s_prefix_n + excl_n, be = s_prefix_e + excl_e;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    const int s = s_begin + k;
+    if (s < n_samples) {
+      xo[base + s] = (float)(bn + vn[k]);
+      yo[base + s] = (float)(be + ve[k]);
+    }
+  }
+}
+
+int pose_scan_tile() { return kScanTile; }
+int pose_scan_threads() { return kScanThreads; }
+size_t pose_scan_state_bytes() { return sizeof(ScanState); }
+
+// ===========================================================================
+// ray set-up
+// ===========================================================================
+//
+// grid.x = n_flights * groups_per_flight; block = 1024 = 32 frames x 32 beams.
+// kind == nullptr: every entry is a frame (pose + 32 ranges).
+// kind[i] == 1   : entry i is one raw ray raycast_update(x0,y0,x1,y1,hit) stored as
+//                  x=x0, y=y0, yaw=x1, ranges[0]=y1, ranges[1]=hit (drop-in symbol only).
+__global__ void __launch_bounds__(1024)
+k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __restrict__ x,
+            const float* __restrict__ y, const float* __restrict__ yaw_deg,
+            const float* __restrict__ ranges, const uint8_t* __restrict__ kind,
+            uint4* __restrict__ frames, uint2* __restrict__ groups, uint2* __restrict__ rays,
+            unsigned long long* __restrict__ stats /* [4]: U, accepted, skipped, domain */) {
+  __shared__ int s_box[4][32];
+  __shared__ unsigned long long s_cnt[4][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int flight = blockIdx.x / groups_per_flight;
+  const int g = blockIdx.x % groups_per_flight;
+  const int f = g * 32 + w;
+  const size_t fbase = (size_t)flight * n_frames;
+
+  int xmin = 0x7fff, xmax = 0, ymin = 0x7fff, ymax = 0;
+  unsigned long long cells = 0;
+  int accepted = 0, skipped = 0, domain = 0;
+
+  if (f < n_frames) {
+    const size_t fi = fbase + f;
+    const float px = x[fi], py = y[fi], third = yaw_deg[fi];
+    const bool raw = kind != nullptr && kind[fi] == 1;
+    int gx0, gy0;
+    const bool have_o = world_to_grid(p, px, py, gx0, gy0);
+    float ex = 0.f, ey = 0.f;
+    bool hit = false;
+    int st;
+    if (!raw) {
+      st = beam_endpoint(p, px, py, third, ranges[fi * 32 + lane], lane, ex, ey, hit);
+    } else {
+      st = (lane == 0) ? 1 : 0;
+      ex = third;
+      ey = ranges[fi * 32 + 0];
+      hit = ranges[fi * 32 + 1] != 0.0f;
+    }
+    uint32_t w0 = 0, w1 = 0;
+    if (st < 0) {
+      domain = 1;
+    } else if (st > 0 && have_o) {
+      int gx1, gy1;
+      if (world_to_grid(p, ex, ey, gx1, gy1)) {
+        const int dx = gx1 - gx0, dy = gy1 - gy0;
+        const int m = max(abs(dx), abs(dy));
+        if (m > kMaxRayCells) {
+          domain = 1;
+        } else {
+          w0 = ((uint32_t)dx & 0xfffu) | (((uint32_t)dy & 0xfffu) << 12) | (hit ? kRayHit : 0u) |
+               kRayValid;
+          w1 = m ? (uint32_t)(((1ull << 31) + (unsigned)m - 1) / (unsigned)m) : 0u;
+          xmin = min(gx0, gx1); xmax = max(gx0, gx1);
+          ymin = min(gy0, gy1); ymax = max(gy0, gy1);
+          cells = (unsigned long long)m + 1;
+          accepted = 1;
+        }
+      }
+    }
+    if (!accepted && !domain && !(raw && lane != 0)) skipped = 1;
+    rays[fi * 32 + lane] = make_uint2(w0, w1);
+
+    xmin = __reduce_min_sync(0xffffffffu, xmin);
+    xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin);
+    ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if (lane == 0)
+      frames[fi] = make_uint4(have_o ? (uint32_t)gx0 : 0xffffffffu, have_o ? (uint32_t)gy0 : 0xffffffffu,
+                              (uint32_t)xmin | ((uint32_t)xmax << 16),
+                              (uint32_t)ymin | ((uint32_t)ymax << 16));
+  }
+  // per-warp counters, then one block-level reduce by warp 0
+  unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)accepted);
+  unsigned s = __reduce_add_sync(0xffffffffu, (unsigned)skipped);
+  unsigned d = __reduce_add_sync(0xffffffffu, (unsigned)domain);
+  unsigned c32 = __reduce_add_sync(0xffffffffu, (unsigned)cells);   // <= 32*1025 per warp
+  if (lane == 0) {
+    s_box[0][w] = xmin; s_box[1][w] = xmax; s_box[2][w] = ymin; s_box[3][w] = ymax;
+    s_cnt[0][w] = c32; s_cnt[1][w] = a; s_cnt[2][w] = s; s_cnt[3][w] = d;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int bx0 = __reduce_min_sync(0xffffffffu, s_box[0][lane]);
+    const int bx1 = __reduce_max_sync(0xffffffffu, s_box[1][lane]);
+    const int by0 = __reduce_min_sync(0xffffffffu, s_box[2][lane]);
+    const int by1 = __reduce_max_sync(0xffffffffu, s_box[3][lane]);
+    if (lane == 0)
+      groups[(size_t)flight * groups_per_flight + g] =
+          make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
+    if (lane < 4) {
+      unsigned long long t = 0;
+      for (int i = 0; i < 32; i++) t += s_cnt[lane][i];
+      if (t) atomicAdd(&stats[lane], t);
+    }
+  }
+}
+
+// Parity hook: end cell of every beam from the records (cells [-1,-1] when skipped).
+__global__ void k_records_to_cells(long long n_frames, const uint4* __restrict__ frames,
+                                   const uint2* __restrict__ rays, int32_t* __restrict__ cells,
+                                   int32_t* __restrict__ origin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames * 32) return;
+  const long long f = i >> 5;
+  const uint4 fr = frames[f];
+  const uint2 r = rays[i];
+  int cx = -1, cy = -1;
+  if (r.x & kRayValid) {
+    cx = (int)fr.x + sext12(r.x);
+    cy = (int)fr.y + sext12(r.x >> 12);
+  }
+  cells[2 * i] = cx;
+  cells[2 * i + 1] = cy;
+  if ((i & 31) == 0) {
+    origin[2 * f] = (int)fr.x;
+    origin[2 * f + 1] = (int)fr.y;
+  }
+}
+
+__global__ void k_sincosf(size_t n, const float* __restrict__ a, float* __restrict__ s,
+                          float* __restrict__ c) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float sn, cs;
+  sincosf_glibc(a[i], sn, cs);
+  s[i] = sn;
+  c[i] = cs;
+}
+
+// world_to_grid() for the drop-in symbol: one thread, result in mapped host memory.
+__global__ void k_world_to_grid_one(DevParams p, float wx, float wy, int* out /* [3] */) {
+  int gx, gy;
+  const bool ok = world_to_grid(p, wx, wy, gx, gy);
+  out[0] = ok ? 1 : 0;
+  out[1] = gx;
+  out[2] = gy;
+}
+
+// ===========================================================================
+// replay: persistent warps owning shared-memory sub-tiles
+// ===========================================================================
+
+__device__ __forceinline__ bool box_overlaps(uint32_t xlohi, uint32_t ylohi, int X0, int X1, int Y0,
+                                             int Y1) {
+  const int bx0 = (int)(xlohi & 0xffffu), bx1 = (int)(xlohi >> 16);
+  const int by0 = (int)(ylohi & 0xffffu), by1 = (int)(ylohi >> 16);
+  return bx0 < X1 && bx1 >= X0 && by0 < Y1 && by1 >= Y0;
+}
+
+// Apply, in beam order, the part of every ray of one frame that lies inside the warp's
+// sub-tile [X0,X1) x [Y0,Y1).  Lane b first clips beam b (closed-form Bresenham, see
+// cell k of a ray is major0 + k*s_major, minor0 + s_minor*floor((k*n+m/2)/m));
+// then the warp walks the surviving rays one by one with lanes along the ray.
+__device__ __forceinline__ void apply_frame(const ReplayArgs& A, int8_t* tile, int lane, int gx0,
+                                            int gy0, uint2 rec, int X0, int X1, int Y0, int Y1) {
+  // ---- clip beam `lane` against the sub-tile ---------------------------------------
+  int ka = 0, kb = -1;
+  {
+    const int dx = sext12(rec.x), dy = sext12(rec.x >> 12);
+    const int adx = abs(dx), ady = abs(dy);
+    const bool xmaj = adx >= ady;
+    const int m = xmaj ? adx : ady, n = xmaj ? ady : adx;
+    const int c0 = xmaj ? gx0 : gy0, sM = xmaj ? (dx >= 0 ? 1 : -1) : (dy >= 0 ? 1 : -1);
+    const int A0 = xmaj ? X0 : Y0, A1 = xmaj ? X1 : Y1;
+    const int lo = (sM > 0) ? (A0 - c0) : (c0 - (A1 - 1));
+    const int hi = (sM > 0) ? (A1 - 1 - c0) : (c0 - A0);
+    ka = max(lo, 0);
+    kb = min(hi, m);
+    if (!(rec.x & kRayValid)) kb = -1;
+    if (ka <= kb) {
+      const int n2 = 2 * n, h2 = 2 * (m >> 1);
+      const int qa = minor_steps(ka, n2, h2, rec.y), qb = minor_steps(kb, n2, h2, rec.y);
+      const int c1 = xmaj ? gy0 : gx0, sN = xmaj ? (dy >= 0 ? 1 : -1) : (dx >= 0 ? 1 : -1);
+      const int ma = c1 + sN * qa, mb = c1 + sN * qb;
+      const int B0 = xmaj ? Y0 : X0, B1 = xmaj ? Y1 : X1;
+      if (max(ma, mb) < B0 || min(ma, mb) >= B1) kb = -1;
+    }
+  }
+  unsigned active = __ballot_sync(0xffffffffu, ka <= kb);
+  const int tw = X1 - X0, th = Y1 - Y0;
+  const int bx = gx0 - X0, by = gy0 - Y0;
+  // ---- rays in beam order, lanes along the ray ------------------------------------------
+  while (active) {
+    const int b = __ffs(active) - 1;
+    active &= active - 1;
+    const uint32_t w0 = __shfl_sync(0xffffffffu, rec.x, b);
+    const uint32_t inv = __shfl_sync(0xffffffffu, rec.y, b);
+    const int k0 = __shfl_sync(0xffffffffu, ka, b);
+    const int k1 = __shfl_sync(0xffffffffu, kb, b);
+    const int dx = sext12(w0), dy = sext12(w0 >> 12);
+    const int adx = abs(dx), ady = abs(dy);
+    const bool xmaj = adx >= ady;
+    const int m = xmaj ? adx : ady, n = xmaj ? ady : adx;
+    const int n2 = 2 * n, h2 = 2 * (m >> 1);
+    const int sx = dx >= 0 ? 1 : -1, sy = dy >= 0 ? 1 : -1;
+    const int end_delta = (w0 & kRayHit) ? A.lo_occ : A.end_nohit;
+    for (int k = k0 + lane; k <= k1; k += 32) {
+      const int q = minor_steps(k, n2, h2, inv);
+      const int lx = bx + sx * (xmaj ? k : q);
+      const int ly = by + sy * (xmaj ? q : k);
+      if ((unsigned)lx < (unsigned)tw && (unsigned)ly < (unsigned)th) {
+        int8_t* cell = tile + ly * A.pitch + lx;
+        const int delta = (k == m) ? end_delta : -A.lo_free;
+        int v = (int)*cell + delta;
+        v = max(v, A.lo_min);
+        v = min(v, A.lo_max);
+        *cell = (int8_t)v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+extern __shared__ __align__(16) unsigned char uqs_smem[];
+
+__global__ void __launch_bounds__(kReplayThreads)
+k_replay_tiles(ReplayArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
+  int8_t* tile = reinterpret_cast<int8_t*>(uqs_smem) + (size_t)wic * A.tile_bytes;
+  const int subs_per_grid = A.nsx * A.nsy;
+
+  for (;;) {
+    unsigned long long job = 0;
+    if (lane == 0) job = atomicAdd(A.job_counter, 1ull);
+    job = __shfl_sync(0xffffffffu, job, 0);
+    if (job >= A.total_jobs) break;
+    const int flight = (int)(job / subs_per_grid);
+    const int sub = (int)(job % subs_per_grid);
+    const int X0 = (sub % A.nsx) * A.sw, Y0 = A.row0 + (sub / A.nsx) * A.sh;
+    const int X1 = min(X0 + A.sw, A.W), Y1 = min(Y0 + A.sh, A.row0 + A.rows);
+    const int tw = X1 - X0, th = Y1 - Y0;
+    int8_t* grid = A.grids + (size_t)flight * A.W * A.H;
+    const bool vec = ((A.W | X0 | tw) & 3) == 0 && ((reinterpret_cast<size_t>(grid) & 3) == 0);
+
+    // ---- load (accumulate) or clear the sub-tile --------------------------------------
+    if (A.accumulate) {
+      if (vec) {
+        const int wpr = tw >> 2;
+        for (int i = lane; i < wpr * th; i += 32) {
+          const int r = i / wpr, c = i - r * wpr;
+          *reinterpret_cast<uint32_t*>(tile + r * A.pitch + 4 * c) =
+              *reinterpret_cast<const uint32_t*>(grid + (size_t)(Y0 + r) * A.W + X0 + 4 * c);
+        }
+      } else {
+        for (int i = lane; i < tw * th; i += 32) {
+          const int r = i / tw, c = i - r * tw;
+          tile[r * A.pitch + c] = grid[(size_t)(Y0 + r) * A.W + X0 + c];
+        }
+      }
+    } else {
+      for (int i = lane; i < (A.pitch >> 2) * th; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+    }
+    __syncwarp();
+
+    // ---- walk the log in order, culling by group and frame bounding boxes -------------
+    const uint2* groups = A.groups + (size_t)flight * A.groups_per_flight;
+    const uint4* frames = A.frames + (size_t)flight * A.n_frames;
+    const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
+    for (int g0 = 0; g0 < A.groups_per_flight; g0 += 32) {
+      bool ghit = false;
+      if (g0 + lane < A.groups_per_flight) {
+        const uint2 gb = __ldg(&groups[g0 + lane]);
+        ghit = box_overlaps(gb.x, gb.y, X0, X1, Y0, Y1);
+      }
+      unsigned gmask = __ballot_sync(0xffffffffu, ghit);
+      while (gmask) {
+        const int gi = __ffs(gmask) - 1;
+        gmask &= gmask - 1;
+        const int f0 = (g0 + gi) * 32;
+        uint4 fr = make_uint4(0, 0, kEmptyBoxLoHi, kEmptyBoxLoHi);
+        if (f0 + lane < A.n_frames) fr = __ldg(&frames[f0 + lane]);
+        unsigned fmask = __ballot_sync(0xffffffffu, box_overlaps(fr.z, fr.w, X0, X1, Y0, Y1));
+        // software pipeline: the next hit frame's ray records are in flight while this one is applied
+        uint2 rec_next = make_uint2(0, 0);
+        if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
+        while (fmask) {
+          const int fi = __ffs(fmask) - 1;
+          fmask &= fmask - 1;
+          const uint2 rec = rec_next;
+          if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
+          const int gx0 = (int)__shfl_sync(0xffffffffu, fr.x, fi);
+          const int gy0 = (int)__shfl_sync(0xffffffffu, fr.y, fi);
+          apply_frame(A, tile, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- write the sub-tile back --------------------------------------------------------
+    if (vec) {
+      const int wpr = tw >> 2;
+      for (int i = lane; i < wpr * th; i += 32) {
+        const int r = i / wpr, c = i - r * wpr;
+        *reinterpret_cast<uint32_t*>(grid + (size_t)(Y0 + r) * A.W + X0 + 4 * c) =
+            *reinterpret_cast<const uint32_t*>(tile + r * A.pitch + 4 * c);
+      }
+    } else {
+      for (int i = lane; i < tw * th; i += 32) {
+        const int r = i / tw, c = i - r * tw;
+        grid[(size_t)(Y0 + r) * A.W + X0 + c] = tile[r * A.pitch + c];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ===========================================================================
+// on-chip RMW ceiling: the same byte read-modify-write as apply_frame(), with
+// conflict-free addresses and no ray arithmetic.
+// ===========================================================================
+__global__ void __launch_bounds__(kReplayThreads)
+k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink) {
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  int8_t* tile = reinterpret_cast<int8_t*>(uqs_smem) + (size_t)wic * tile_bytes;
+  for (int i = lane; i < tile_bytes; i += 32) tile[i] = 0;
+  __syncwarp();
+  const int span = tile_bytes / 32;          // each lane walks its own 4-byte-aligned words
+  int off = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 8
+    for (int u = 0; u < 8; u++) {
+      int8_t* cell = tile + ((off + u * 37) % span) * 32 + lane;   // 32 consecutive bytes: 8 banks, no conflict
+      int v = (int)*cell - 1;
+      v = max(v, lo_min);
+      *cell = (int8_t)v;
+    }
+    off += 8 * 37;
+  }
+  __syncwarp();
+  if (tile[lane] == 77) *sink = 1;
+}
+
+}  // namespace uqs

@@ -1,0 +1,52 @@
+// uqs_kernels.cuh -- kernel argument blocks and prototypes shared by the host layer.
+#pragma once
+#include "uqs_device.cuh"
+
+namespace uqs {
+
+constexpr int kReplayThreads = 256;               // 8 warps per CTA, each owning one sub-tile
+constexpr int kReplayWarps = kReplayThreads / 32;
+
+struct ReplayArgs {
+  const uint4* frames;      // [n_flights][n_frames]
+  const uint2* groups;      // [n_flights][groups_per_flight]  bbox of 32 consecutive frames
+  const uint2* rays;        // [n_flights][n_frames][32]
+  int8_t* grids;            // [n_flights][H][W]
+  unsigned long long* job_counter;
+  unsigned long long total_jobs;
+  int n_frames, groups_per_flight;
+  int W, H;
+  int row0, rows;           // rows of the grid this launch owns
+  int sw, sh, nsx, nsy;     // sub-tile size and count per grid
+  int pitch, tile_bytes;    // shared-memory row pitch (bytes, odd number of words) and tile size
+  int lo_free, lo_occ, lo_min, lo_max, end_nohit;
+  int accumulate;
+};
+
+struct ScanState;
+
+__global__ void k_pose_increments(long long total, int n_samples, const uint32_t* t_ms,
+                                  const float* rate_x, const float* rate_y, const float* h_m,
+                                  const float* yaw_deg, const uint8_t* q, float deg2rad, float* inc_n,
+                                  float* inc_e, unsigned long long* domain_errors);
+__global__ void k_pose_chain(int n_flights, int n_samples, const float* inc_n, const float* inc_e,
+                             float* xo, float* yo);
+__global__ void k_pose_scan(int n_flights, int n_samples, int parts_per_flight, const float* inc_n,
+                            const float* inc_e, float* xo, float* yo, volatile ScanState* state,
+                            unsigned int* ticket);
+int pose_scan_tile();
+size_t pose_scan_state_bytes();
+int pose_scan_threads();
+
+__global__ void k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* x,
+                            const float* y, const float* yaw_deg, const float* ranges,
+                            const uint8_t* kind, uint4* frames, uint2* groups, uint2* rays,
+                            unsigned long long* stats);
+__global__ void k_records_to_cells(long long n_frames, const uint4* frames, const uint2* rays,
+                                   int32_t* cells, int32_t* origin);
+__global__ void k_sincosf(size_t n, const float* a, float* s, float* c);
+__global__ void k_world_to_grid_one(DevParams p, float wx, float wy, int* out);
+__global__ void k_replay_tiles(ReplayArgs A);
+__global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);
+
+}  // namespace uqs
