@@ -99,6 +99,11 @@ int  uqs_set_stream(void* cuda_stream);
 int  uqs_use_own_stream(void);
 /* Number of kernels this library has launched so far (bench.py's gpu_launches). */
 unsigned long long uqs_kernel_launches(void);
+/* Per-kernel device timing with events on the launching stream.  uqs_profile_collect()
+ * returns the summed device time (ms) and launch count per kernel family since the last
+ * call -- [0] pose integration, [1] ray set-up, [2] replay -- and synchronises. */
+int  uqs_set_profiling(int on);
+int  uqs_profile_collect(double ms[3], int counts[3]);
 /* Block until everything enqueued so far has finished. */
 int  uqs_sync(void);
 
@@ -106,6 +111,11 @@ int  uqs_sync(void);
  * cells one warp owns in shared memory; time_slices > 1 splits a flight's frames
  * into contiguous slices that are replayed concurrently and composed exactly. */
 int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
+/* Replay engine: 0 = automatic (grid resident in one CTA's shared memory when W*H fits
+ * 227 KB, warp-owned sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
+ * (error if it does not fit).  flight_warps = warps per CTA of the resident engine
+ * (0, 8, 16 or 32).  Both engines produce identical bytes. */
+int  uqs_set_engine(int engine, int flight_warps);
 
 /*
  * P0 -- dead-reckoning pose integration (BUILDER-DEFINED: the reference has no

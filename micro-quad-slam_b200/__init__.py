@@ -79,7 +79,8 @@ _lib = None
 _EXPORTS = [
     # batch API
     "uqs_params_default", "uqs_init", "uqs_shutdown", "uqs_last_error", "uqs_device_sm_count",
-    "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_kernel_launches",
+    "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_kernel_launches",
+    "uqs_set_profiling", "uqs_profile_collect",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
     "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
     # drop-in symbols
@@ -107,6 +108,9 @@ def lib() -> C.CDLL:
     L.uqs_init.argtypes = [ip]
     L.uqs_set_stream.argtypes = [vp]
     L.uqs_set_tuning.argtypes = [ip, ip, ip]
+    L.uqs_set_engine.argtypes = [ip, ip]
+    L.uqs_set_profiling.argtypes = [ip]
+    L.uqs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.uqs_kernel_launches.restype = C.c_ulonglong
     L.uqs_pose_integrate.argtypes = [ip, ip] + [vp] * 8 + [ip]
     L.uqs_pose_integrate_dev.argtypes = [ip, ip] + [vp] * 8 + [ip]
@@ -158,6 +162,22 @@ def set_tuning(subtile_w: int = 0, subtile_h: int = 0, time_slices: int = 0):
     _check(lib().uqs_set_tuning(subtile_w, subtile_h, time_slices))
 
 
+def set_engine(engine: int = 0, flight_warps: int = 0):
+    """0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA (identical results)."""
+    _check(lib().uqs_set_engine(engine, flight_warps))
+
+
+def set_profiling(on: bool):
+    _check(lib().uqs_set_profiling(1 if on else 0))
+
+
+def profile_collect():
+    """(ms, counts) per kernel family [pose, ray set-up, replay] since the last call; synchronises."""
+    ms, cnt = (C.c_double * 3)(), (C.c_int * 3)()
+    _check(lib().uqs_profile_collect(ms, cnt))
+    return list(ms), list(cnt)
+
+
 def kernel_launches() -> int:
     return int(lib().uqs_kernel_launches())
 
@@ -191,7 +211,8 @@ def replay(p: Params, x, y, yaw_deg, ranges, out: Optional[np.ndarray] = None):
     return grids, st.as_dict()
 
 
-def replay_flow(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, ranges, want_poses=True):
+def replay_flow(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, ranges, want_poses=True,
+                out: Optional[np.ndarray] = None):
     """``uqs_replay_flow``: P0 then the replay, one frame per flow sample."""
     t_ms = np.ascontiguousarray(t_ms, dtype=np.uint32)
     if t_ms.ndim == 1:
@@ -200,7 +221,7 @@ def replay_flow(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, range
     rx, ry, h, yaw = (_f32(a).reshape(F, N) for a in (of_rate_x, of_rate_y, h_m, yaw_deg))
     q = np.ascontiguousarray(of_q, dtype=np.uint8).reshape(F, N)
     ranges = _f32(ranges).reshape(F, N, BEAMS_PER_FRAME)
-    grids = np.empty((F, p.H, p.W), np.int8)
+    grids = out if out is not None else np.empty((F, p.H, p.W), np.int8)
     px = np.empty((F, N), np.float32) if want_poses else None
     py = np.empty((F, N), np.float32) if want_poses else None
     st = Stats()

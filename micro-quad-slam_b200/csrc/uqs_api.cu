@@ -125,7 +125,25 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   int pitch = (sw + 3) & ~3;
   if (((pitch >> 2) & 1) == 0) pitch += 4;            // odd word pitch: column walks hit 32 banks
   const int tile_bytes = pitch * sh;
-  const size_t smem = (size_t)tile_bytes * kReplayWarps;
+  size_t smem = (size_t)tile_bytes * kReplayWarps;
+
+  // engine: whole grid resident in one CTA's shared memory (frame-synchronous) when it fits
+  // and the launch owns the whole grid; otherwise warp-owned sub-tiles
+  int fpitch = (dp.W + 3) & ~3;
+  if (((fpitch >> 2) & 1) == 0 && (size_t)(fpitch + 4) * dp.H <= kFlightSmemMax) fpitch += 4;
+  const int nw = g_ctx.flight_warps == 8 ? 8 : (g_ctx.flight_warps == 32 ? 32 : 16);
+  int ring_size = 256;                                    // per-warp collision table (power of two)
+  while (ring_size > 32 && (size_t)fpitch * dp.H + (size_t)ring_size * nw > kFlightSmemMax) ring_size >>= 1;
+  const size_t fsmem = (size_t)fpitch * dp.H + (size_t)ring_size * nw;
+  // auto: the frame-synchronous resident engine wins while flights are too few to fill the chip with
+  // independent sub-tile warps (measured crossover ~4 flights per SM); beyond that sub-tiles win
+  const bool fits = row0 == 0 && rows == dp.H && fsmem <= kFlightSmemMax;
+  const bool resident = fits && (g_ctx.engine == 2 || (g_ctx.engine == 0 && n_flights <= 4 * g_ctx.sm_count));
+  if (g_ctx.engine == 2 && !fits) {
+    set_error("engine 2 (grid resident per CTA) needs the whole %dx%d grid in %zu B of shared memory", dp.W, dp.H, kFlightSmemMax);
+    return UQS_ERR_BAD_ARG;
+  }
+  if (resident) smem = fsmem;
   if (smem > 227u * 1024u) {
     set_error("sub-tile %dx%d needs %zu B of shared memory per CTA (> 227 KB)", sw, sh, smem);
     return UQS_ERR_BAD_ARG;
@@ -147,22 +165,50 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     if (e != cudaSuccess) return cuda_fail(e, "memset stats");
   }
 
-  e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");
   int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_replay_tiles, kReplayThreads, smem);
-  if (e != cudaSuccess) return cuda_fail(e, "occupancy(k_replay_tiles)");
-  if (ctas_per_sm < 1) { set_error("k_replay_tiles does not fit on an SM (smem %zu)", smem); return UQS_ERR_CUDA; }
+  if (resident) {
+    e = flights_prepare(nw, smem, &ctas_per_sm);
+    if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights attributes");
+  } else {
+    e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_replay_tiles, kReplayThreads, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy(k_replay_tiles)");
+  }
+  if (ctas_per_sm < 1) { set_error("replay kernel does not fit on an SM (smem %zu)", smem); return UQS_ERR_CUDA; }
 
   for (int f0 = 0; f0 < n_flights; f0 += chunk) {
     const int nf = std::min(chunk, n_flights - f0);
     const size_t fo = (size_t)f0 * n_frames;
+    KernelTimer t_setup(1);
     k_ray_setup<<<(unsigned)(nf * gpf), 1024, 0, st>>>(
         dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr,
         (uint4*)g_ctx.ws_frames.p, (uint2*)g_ctx.ws_groups.p, (uint2*)g_ctx.ws_rays.p, counters);
     e = cudaGetLastError();
+    t_setup.stop();
     if (e != cudaSuccess) return cuda_fail(e, "k_ray_setup launch");
 
+    if (resident) {
+      FlightArgs FA;
+      FA.frames = (const uint4*)g_ctx.ws_frames.p;
+      FA.rays = (const uint2*)g_ctx.ws_rays.p;
+      FA.grids = grids + (size_t)f0 * dp.W * dp.H;
+      FA.job_counter = counters + 8;
+      FA.n_flights = nf; FA.n_frames = n_frames;
+      FA.W = dp.W; FA.H = dp.H; FA.pitch = fpitch; FA.ring_size = ring_size;
+      FA.lo_free = dp.lo_free; FA.lo_occ = dp.lo_occ; FA.lo_min = dp.lo_min; FA.lo_max = dp.lo_max;
+      FA.end_nohit = dp.end_nohit;
+      FA.accumulate = accumulate;
+      e = cudaMemsetAsync(FA.job_counter, 0, sizeof(unsigned long long), st);
+      if (e != cudaSuccess) return cuda_fail(e, "memset job counter");
+      const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)ctas_per_sm * g_ctx.sm_count);
+      KernelTimer t_rep(2);
+      e = flights_launch(nw, fgrid, smem, st, FA);
+      t_rep.stop();
+      if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights launch");
+      g_ctx.launches += 2;
+      continue;
+    }
     ReplayArgs A;
     A.frames = (const uint4*)g_ctx.ws_frames.p;
     A.groups = (const uint2*)g_ctx.ws_groups.p;
@@ -181,8 +227,10 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     if (e != cudaSuccess) return cuda_fail(e, "memset job counter");
     unsigned long long want = (A.total_jobs + kReplayWarps - 1) / kReplayWarps;
     unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctas_per_sm * g_ctx.sm_count);
+    KernelTimer t_rep(2);
     k_replay_tiles<<<grid, kReplayThreads, smem, st>>>(A);
     e = cudaGetLastError();
+    t_rep.stop();
     if (e != cudaSuccess) return cuda_fail(e, "k_replay_tiles launch");
     g_ctx.launches += 2;
   }
@@ -222,6 +270,7 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
   if (e != cudaSuccess) return cuda_fail(e, "memset pose counter");
   volatile float pi_f = (float)M_PI;
   const float deg2rad = pi_f / 180.0f;
+  KernelTimer t_pose(0);
   k_pose_increments<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, n_samples, t_ms, rx, ry, h, yaw, q,
                                                                      deg2rad, inc_n, inc_e, dom);
   e = cudaGetLastError();
@@ -242,6 +291,7 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
                                                                   (volatile ScanState*)g_ctx.ws_scan.p, ticket);
   }
   e = cudaGetLastError();
+  t_pose.stop();
   if (e != cudaSuccess) return cuda_fail(e, "pose kernel launch");
   g_ctx.launches += 2;
   return UQS_OK;
@@ -339,7 +389,42 @@ int uqs_set_tuning(int sw, int sh, int time_slices) {
   return UQS_OK;
 }
 
+int uqs_set_engine(int engine, int flight_warps) {
+  if (engine < 0 || engine > 2 || (flight_warps != 0 && flight_warps != 8 && flight_warps != 16 && flight_warps != 32)) {
+    set_error("engine must be 0 (auto), 1 (sub-tiles) or 2 (grid resident); warps 0, 8, 16 or 32");
+    return UQS_ERR_BAD_ARG;
+  }
+  g_ctx.engine = engine;
+  g_ctx.flight_warps = flight_warps;
+  return UQS_OK;
+}
+
 unsigned long long uqs_kernel_launches(void) { return g_ctx.launches; }
+
+int uqs_set_profiling(int on) {
+  int rc = check_ready();
+  if (rc) return rc;
+  g_ctx.profiling = on != 0;
+  return UQS_OK;
+}
+
+/* Sum of device time per kernel family since the last call (ms): [0] pose, [1] ray set-up,
+ * [2] replay; counts[] = launches of each.  Synchronises the stream. */
+int uqs_profile_collect(double ms[3], int counts[3]) {
+  int rc = check_ready();
+  if (rc) return rc;
+  cudaError_t e = cudaStreamSynchronize(g_ctx.stream());
+  if (e != cudaSuccess) return cuda_fail(e, "profile sync");
+  for (int i = 0; i < 3; i++) { ms[i] = 0.0; counts[i] = 0; }
+  for (auto& s : g_ctx.spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ms[s.kind] += t; counts[s.kind]++; }
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  g_ctx.spans.clear();
+  return UQS_OK;
+}
 
 int uqs_replay_dev(const uqs_params* p, int n_flights, int n_frames, const float* x, const float* y,
                    const float* yaw, const float* ranges, int8_t* grids, int accumulate, int row0,

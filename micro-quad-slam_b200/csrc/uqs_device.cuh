@@ -23,12 +23,14 @@ struct DevParams {
 
 // Ray record, 8 bytes:  w0 = dx[12 signed] | dy[12 signed]<<12 | hit<<24 | valid<<25
 //                       w1 = ceil(2^31 / m), m = max(|dx|,|dy|)  (0 when m == 0)
-// Frame record, 16 bytes: x = origin cell gx, y = gy (or -1,-1),
+// Frame record, 16 bytes: x = origin cell gx | K0<<16, y = gy | kFrameHasOrigin
+//                         (K0: beams of the frame can share a cell only at steps k < K0),
 //                         z = xmin | xmax<<16, w = ymin | ymax<<16  (bbox of all cells the
 //                         frame's accepted rays touch; empty bbox = min 0x7fff, max 0)
 constexpr int      kMaxRayCells   = 1024;       // magic-division exactness bound
 constexpr uint32_t kRayHit        = 1u << 24;
 constexpr uint32_t kRayValid      = 1u << 25;
+constexpr uint32_t kFrameHasOrigin = 1u << 16;
 constexpr uint32_t kEmptyBoxLoHi  = 0x00007fffu;  // min = 0x7fff, max = 0  -> never overlaps
 
 // ---------------------------------------------------------------------------

@@ -245,12 +245,44 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
     if (!accepted && !domain && !(raw && lane != 0)) skipped = 1;
     rays[fi * 32 + lane] = make_uint2(w0, w1);
 
+    // K0: two accepted beams of this frame can share a cell only at steps k < K0 (DESIGN.md,
+    // "same-k lemma" and ring coordinate).  sigma = position of the beam's direction on the
+    // unit max-norm ring, in [0,8); cells of step k sit within 1/2 of k*sigma on the ring of
+    // radius k, so beams i,j are apart for every k > 1/|sigma_i - sigma_j|.  Conservative
+    // float arithmetic (K0 may only be too large) -- it gates a fast path, never a result.
+    int k0 = 0;
+    {
+      const int dx = sext12(w0), dy = sext12(w0 >> 12);
+      const int adx = abs(dx), ady = abs(dy);
+      const bool xmaj = adx >= ady;
+      const int m = accepted ? (xmaj ? adx : ady) : -1;
+      const int n = xmaj ? ady : adx;
+      const bool xpos = dx >= 0, ypos = dy >= 0;
+      float ra, rb;
+      if (xmaj) { ra = xpos ? (ypos ? 0.f : 8.f) : 4.f; rb = (xpos == ypos) ? 1.f : -1.f; }
+      else      { ra = ypos ? 2.f : 6.f;                rb = (xpos == ypos) ? -1.f : 1.f; }
+      const float sigma = (m > 0) ? ra + rb * ((float)n / (float)m) : 0.f;
+#pragma unroll 4
+      for (int j = 1; j <= 16; j++) {
+        const int pl = (lane + j) & 31;
+        const float sp = __shfl_sync(0xffffffffu, sigma, pl);
+        const int mp = __shfl_sync(0xffffffffu, m, pl);
+        float dlt = fabsf(sigma - sp);
+        dlt = fminf(dlt, 8.f - dlt);
+        int kk = (dlt > 1e-4f) ? (int)(1.0f / (dlt - 2e-5f)) + 2 : 0x7fffffff;
+        kk = min(kk, min(m, mp) + 1);          // a beam has no step beyond its own length
+        if (m >= 0 && mp >= 0) k0 = max(k0, kk);
+      }
+      k0 = __reduce_max_sync(0xffffffffu, k0);
+    }
+
     xmin = __reduce_min_sync(0xffffffffu, xmin);
     xmax = __reduce_max_sync(0xffffffffu, xmax);
     ymin = __reduce_min_sync(0xffffffffu, ymin);
     ymax = __reduce_max_sync(0xffffffffu, ymax);
     if (lane == 0)
-      frames[fi] = make_uint4(have_o ? (uint32_t)gx0 : 0xffffffffu, have_o ? (uint32_t)gy0 : 0xffffffffu,
+      frames[fi] = make_uint4(have_o ? ((uint32_t)gx0 | ((uint32_t)k0 << 16)) : 0u,
+                              have_o ? ((uint32_t)gy0 | kFrameHasOrigin) : 0u,
                               (uint32_t)xmin | ((uint32_t)xmax << 16),
                               (uint32_t)ymin | ((uint32_t)ymax << 16));
   }
@@ -291,14 +323,14 @@ __global__ void k_records_to_cells(long long n_frames, const uint4* __restrict__
   const uint2 r = rays[i];
   int cx = -1, cy = -1;
   if (r.x & kRayValid) {
-    cx = (int)fr.x + sext12(r.x);
-    cy = (int)fr.y + sext12(r.x >> 12);
+    cx = (int)(fr.x & 0xffffu) + sext12(r.x);
+    cy = (int)(fr.y & 0xffffu) + sext12(r.x >> 12);
   }
   cells[2 * i] = cx;
   cells[2 * i + 1] = cy;
   if ((i & 31) == 0) {
-    origin[2 * f] = (int)fr.x;
-    origin[2 * f + 1] = (int)fr.y;
+    origin[2 * f] = (fr.y & kFrameHasOrigin) ? (int)(fr.x & 0xffffu) : -1;
+    origin[2 * f + 1] = (fr.y & kFrameHasOrigin) ? (int)(fr.y & 0xffffu) : -1;
   }
 }
 
@@ -464,8 +496,8 @@ k_replay_tiles(ReplayArgs A) {
           fmask &= fmask - 1;
           const uint2 rec = rec_next;
           if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
-          const int gx0 = (int)__shfl_sync(0xffffffffu, fr.x, fi);
-          const int gy0 = (int)__shfl_sync(0xffffffffu, fr.y, fi);
+          const int gx0 = (int)(__shfl_sync(0xffffffffu, fr.x, fi) & 0xffffu);
+          const int gy0 = (int)(__shfl_sync(0xffffffffu, fr.y, fi) & 0xffffu);
           apply_frame(A, tile, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
         }
       }
@@ -488,6 +520,229 @@ k_replay_tiles(ReplayArgs A) {
     }
     __syncwarp();
   }
+}
+
+// ===========================================================================
+// replay, whole grid resident: one CTA per flight, frame-synchronous
+// ===========================================================================
+//
+// For grids that fit one CTA's shared memory (<= 227 KB: every 400x400 ensemble member,
+// config 5 up to 476x476).  Exactness argument (DESIGN.md "same-k lemma"): all beams of a
+// frame start in the same cell, and cell k of a beam is
+//     ( x0 + sgn(dx)*rnd(k*|dx|/m),  y0 + sgn(dy)*rnd(k*|dy|/m) ),   rnd(u) = floor(u + 1/2),
+// so two beams of one frame can only meet in a cell at the SAME step index k.  The 32 lanes
+// of a warp are the 32 beams, and a warp instruction applies step k of all of them at once:
+// every intra-frame collision is then inside one instruction; it is detected through a
+// per-warp table indexed by ring position (match.any serialises over distinct values and is
+// ~10x too slow here) and serialised in lane (= beam = reference) order.  Warps take interleaved k; steps with
+// different k never touch the same cell, so warps need no ordering inside a frame, and one
+// barrier per frame keeps frames in log order.
+// per-lane (= per-beam) state of one frame in the resident engine
+struct Beam {
+  int m;            // steps 0..m (-1: beam skipped)
+  int n2;           // 2 * minor extent
+  uint32_t inv;     // ceil(2^31 / m)
+  int sM, sN;       // byte stride of a major / minor step in the resident grid
+  int ra, rb;       // ring position of step k: ra*k + rb*q
+  int end_delta;    // +occ on a hit, -(free/2) otherwise
+  int base;         // byte offset of the frame's origin cell
+  int k0;           // shared-step bound of the frame
+};
+
+__device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int lo_occ, int end_nohit) {
+  Beam b;
+  const int dx = sext12(rec.x), dy = sext12(rec.x >> 12);
+  const int adx = abs(dx), ady = abs(dy);
+  const bool xmaj = adx >= ady;
+  b.m = (rec.x & kRayValid) ? (xmaj ? adx : ady) : -1;
+  b.n2 = 2 * (xmaj ? ady : adx);
+  b.inv = rec.y;
+  const bool xpos = dx >= 0, ypos = dy >= 0;
+  const int sx = xpos ? 1 : -1, sy = ypos ? P : -P;
+  b.sM = xmaj ? sx : sy;
+  b.sN = xmaj ? sy : sx;
+  if (xmaj) { b.ra = xpos ? (ypos ? 0 : 8) : 4; b.rb = (xpos == ypos) ? 1 : -1; }
+  else      { b.ra = ypos ? 2 : 6;              b.rb = (xpos == ypos) ? -1 : 1; }
+  b.end_delta = (rec.x & kRayHit) ? lo_occ : end_nohit;
+  b.base = (int)(org.y & 0xffffu) * P + (int)(org.x & 0xffffu);
+  b.k0 = (int)(org.x >> 16);
+  return b;
+}
+
+// one saturating update of a resident cell
+__device__ __forceinline__ void rmw_cell(int8_t* cell, int delta, int lo_min, int lo_max) {
+  int v = (int)*cell + delta;
+  v = min(max(v, lo_min), lo_max);
+  *cell = (int8_t)v;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_replay_flights(FlightArgs A) {
+  int8_t* grid_s = reinterpret_cast<int8_t*>(uqs_smem);
+  __shared__ int s_flight;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int P = A.pitch;
+  const int words = (P * A.H) >> 2;
+  // per-warp collision table, indexed by the position of a cell on the max-norm ring of
+  // radius k (all step-k cells of a frame lie on that ring; the map cell -> position is injective)
+  uint8_t* ring = reinterpret_cast<uint8_t*>(uqs_smem) + (size_t)P * A.H + (size_t)w * A.ring_size;
+  const int ring_mask = A.ring_size - 1;
+
+  for (;;) {
+    if (threadIdx.x == 0) s_flight = (int)atomicAdd(A.job_counter, 1ull);
+    __syncthreads();
+    const int flight = s_flight;
+    if (flight >= A.n_flights) break;
+    int8_t* grid_g = A.grids + (size_t)flight * A.W * A.H;
+    const bool vec = ((A.W & 3) == 0) && ((reinterpret_cast<size_t>(grid_g) & 3) == 0);
+
+    if (A.accumulate) {
+      if (vec) {
+        const int wpr = A.W >> 2;
+        for (int i = threadIdx.x; i < wpr * A.H; i += NW * 32) {
+          const int r = i / wpr, c = i - r * wpr;
+          reinterpret_cast<uint32_t*>(grid_s + r * P)[c] = reinterpret_cast<const uint32_t*>(grid_g + (size_t)r * A.W)[c];
+        }
+      } else {
+        for (int i = threadIdx.x; i < A.W * A.H; i += NW * 32) {
+          const int r = i / A.W, c = i - r * A.W;
+          grid_s[r * P + c] = grid_g[(size_t)r * A.W + c];
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < words; i += NW * 32) reinterpret_cast<uint32_t*>(grid_s)[i] = 0u;
+    }
+    __syncthreads();
+
+    const uint4* frames = A.frames + (size_t)flight * A.n_frames;
+    const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
+    // two frames of records in flight; beam decode of frame f+1 is issued before the barrier of frame f
+    uint2 rec_n = make_uint2(0u, 0u), org_n = make_uint2(0u, 0u);
+    if (A.n_frames > 1) {
+      rec_n = __ldg(&rays[32 + lane]);
+      org_n = __ldg(reinterpret_cast<const uint2*>(&frames[1]));
+    }
+    Beam B = decode_beam(__ldg(&rays[lane]), __ldg(reinterpret_cast<const uint2*>(&frames[0])), P, A.lo_occ, A.end_nohit);
+    for (int f = 0; f < A.n_frames; f++) {
+      const uint2 rec1 = rec_n, org1 = org_n;
+      if (f + 2 < A.n_frames) {
+        rec_n = __ldg(&rays[(size_t)(f + 2) * 32 + lane]);
+        org_n = __ldg(reinterpret_cast<const uint2*>(&frames[f + 2]));
+      }
+      const int m = B.m, n2 = B.n2, h2 = B.m & ~1, sM = B.sM, sN = B.sN, base = B.base;
+      const uint32_t inv = B.inv;
+      const int mmax = __reduce_max_sync(0xffffffffu, m);
+      const int kshared = min(B.k0, mmax + 1);
+
+      // ---- steps k < K0: beams may meet in a cell; detect and keep beam order --------------------
+      for (int k = w; k < kshared; k += NW) {
+        const bool act = k <= m;
+        const int q = minor_steps(k, n2, h2, inv);
+        const int addr = base + k * sM + q * sN;
+        const int delta = (k == m) ? B.end_delta : -A.lo_free;
+        // runs of consecutive lanes on one cell (beams are ordered by angle, so nearly all
+        // collisions are between neighbours); only the head of a run enters the ring table
+        const unsigned key = act ? (unsigned)addr : (0x80000000u | (unsigned)lane);
+        const unsigned prevkey = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool bound = lane == 0 || prevkey != key;
+        const bool head = act && bound;
+        int pos = B.ra * k + B.rb * q;
+        if (pos == 8 * k) pos = 0;
+        const int slot = pos & ring_mask;
+        if (head) ring[slot] = (uint8_t)lane;
+        __syncwarp();
+        const bool lost = head && ring[slot] != (uint8_t)lane;
+        const unsigned boundm = __ballot_sync(0xffffffffu, bound);
+        const unsigned actm = __ballot_sync(0xffffffffu, act);
+        unsigned pend = __ballot_sync(0xffffffffu, lost);
+        if ((boundm & actm) == actm && pend == 0u) {
+          if (act) rmw_cell(grid_s + addr, delta, A.lo_min, A.lo_max);
+        } else {
+          const unsigned upto = 0xffffffffu >> (31 - lane);               // lanes 0..lane
+          const int start = 31 - __clz(boundm & upto);
+          const unsigned above = boundm & ~upto;
+          const int end = above ? (__ffs(above) - 2) : 31;
+          unsigned peers = (0xffffffffu >> (31 - end)) & (0xffffffffu << start);
+          while (pend) {          // runs that are not neighbours but hit the same cell (rare)
+            const int a = __shfl_sync(0xffffffffu, addr, __ffs(pend) - 1);
+            const bool same = act && addr == a;
+            const unsigned members = __ballot_sync(0xffffffffu, same);
+            pend &= ~members;
+            if (same) peers = members;
+          }
+          const unsigned endm = __ballot_sync(0xffffffffu, act && k == m);
+          const bool uniform = (peers & endm) == 0u;          // only free-space steps in this cell
+          if (act && uniform && lane == __ffs(peers) - 1) {
+            // repeated clamp(v - free) == max(v - cnt*free, lo_min)
+            const int v = (int)grid_s[addr] - __popc(peers) * A.lo_free;
+            grid_s[addr] = (int8_t)max(v, A.lo_min);
+          }
+          const bool mixed = act && !uniform;
+          const int rank = __popc(peers & ((1u << lane) - 1u));
+          const int rounds = __reduce_max_sync(0xffffffffu, mixed ? rank : -1);
+          for (int r = 0; r <= rounds; r++) {
+            if (mixed && rank == r) rmw_cell(grid_s + addr, delta, A.lo_min, A.lo_max);
+            __syncwarp();
+          }
+        }
+        __syncwarp();      // ring[] is rewritten by the next step
+      }
+
+      // ---- steps k >= K0: every cell is touched by one beam only; four steps in flight -------------
+      int k = w + ((max(B.k0 - w, 0) + NW - 1) / NW) * NW;
+      for (; k <= mmax; k += 4 * NW) {
+        int addr[4], val[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int ku = k + u * NW;
+          addr[u] = base + ku * sM + minor_steps(ku, n2, h2, inv) * sN;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (k + u * NW <= m) val[u] = (int)grid_s[addr[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int ku = k + u * NW;
+          if (ku <= m) {
+            const int v = val[u] + ((ku == m) ? B.end_delta : -A.lo_free);
+            grid_s[addr[u]] = (int8_t)min(max(v, A.lo_min), A.lo_max);
+          }
+        }
+      }
+      B = decode_beam(rec1, org1, P, A.lo_occ, A.end_nohit);    // frame f+1, independent of the grid
+      __syncthreads();
+    }
+
+    if (vec) {
+      const int wpr = A.W >> 2;
+      for (int i = threadIdx.x; i < wpr * A.H; i += NW * 32) {
+        const int r = i / wpr, c = i - r * wpr;
+        reinterpret_cast<uint32_t*>(grid_g + (size_t)r * A.W)[c] = reinterpret_cast<const uint32_t*>(grid_s + r * P)[c];
+      }
+    } else {
+      for (int i = threadIdx.x; i < A.W * A.H; i += NW * 32) {
+        const int r = i / A.W, c = i - r * A.W;
+        grid_g[(size_t)r * A.W + c] = grid_s[r * P + c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static void (*flight_kernel(int nw))(FlightArgs) {
+  return nw == 8 ? k_replay_flights<8> : (nw == 32 ? k_replay_flights<32> : k_replay_flights<16>);
+}
+
+cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(flight_kernel(nw), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, flight_kernel(nw), nw * 32, smem);
+}
+
+cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A) {
+  flight_kernel(nw)<<<grid, nw * 32, smem, st>>>(A);
+  return cudaGetLastError();
 }
 
 // ===========================================================================

@@ -23,6 +23,19 @@ struct ReplayArgs {
   int accumulate;
 };
 
+// whole-grid-resident engine: one CTA per flight
+struct FlightArgs {
+  const uint4* frames;
+  const uint2* rays;
+  int8_t* grids;
+  unsigned long long* job_counter;
+  int n_flights, n_frames;
+  int W, H, pitch;
+  int ring_size;            // bytes of collision table per warp (power of two), placed after the grid
+  int lo_free, lo_occ, lo_min, lo_max, end_nohit;
+  int accumulate;
+};
+
 struct ScanState;
 
 __global__ void k_pose_increments(long long total, int n_samples, const uint32_t* t_ms,
@@ -47,6 +60,8 @@ __global__ void k_records_to_cells(long long n_frames, const uint4* frames, cons
 __global__ void k_sincosf(size_t n, const float* a, float* s, float* c);
 __global__ void k_world_to_grid_one(DevParams p, float wx, float wy, int* out);
 __global__ void k_replay_tiles(ReplayArgs A);
+cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm);
+cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);
 
 }  // namespace uqs

@@ -11,6 +11,15 @@ from conftest import first_diff, have_ref
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tiles", "resident8", "resident16", "resident32"])
+def engine(request, gpu):
+    """Both replay engines (and the resident engine's warp counts) must give identical bytes."""
+    e, nw = {"tiles": (1, 0), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[request.param]
+    gpu.set_engine(e, nw)
+    yield request.param
+    gpu.set_engine(0, 0)
+
+
 def oracle_grids(oracle, p, d, x=None, y=None):
     x = d["x_true"] if x is None else x
     y = d["y_true"] if y is None else y
@@ -74,7 +83,7 @@ def test_nonfinite_and_huge_poses_follow_the_reference(gpu, oracle):
 # ----------------------------------------------------------------------------------------------
 # A1-A6: whole replays
 # ----------------------------------------------------------------------------------------------
-def test_c1_single_flight_bit_exact(gpu, oracle, orc_mod, synth):
+def test_c1_single_flight_bit_exact(gpu, oracle, orc_mod, synth, engine):
     w = synth.CONFIGS["c1"]
     d = synth.generate(w)
     p = w.params()
@@ -143,7 +152,7 @@ def test_c4_multizone_sweep_scaled(gpu, oracle, synth):
     assert st["ray_cell_updates"] == U and st["frames"] == 6000
 
 
-@pytest.mark.parametrize("i_res,i_sigma", [(0, 3), (3, 0), (6, 15), (9, 8), (15, 15), (12, 1)])
+@pytest.mark.parametrize("i_res,i_sigma", [(0, 3), (3, 0), (5, 5), (6, 15), (9, 8), (15, 15), (12, 1)])
 def test_c5_resolution_noise_sweep_samples(gpu, oracle, orc_mod, synth, i_res, i_sigma):
     w = synth.c5_workload(i_res, i_sigma, n_flights=3, n_samples=700)
     d = synth.generate(w)
@@ -162,7 +171,7 @@ def test_c5_resolution_noise_sweep_samples(gpu, oracle, orc_mod, synth, i_res, i
 # ----------------------------------------------------------------------------------------------
 # edge cases
 # ----------------------------------------------------------------------------------------------
-def test_ragged_and_degenerate_logs(gpu, oracle, synth):
+def test_ragged_and_degenerate_logs(gpu, oracle, synth, engine):
     """frame counts not a multiple of 32, a single frame, all-skipped frames, poses off the grid."""
     rng = np.random.default_rng(11)
     p = gpu.make_params(236, 236, 0.085, 20.0)
@@ -179,7 +188,7 @@ def test_ragged_and_degenerate_logs(gpu, oracle, synth):
         assert st["ray_cell_updates"] == U
 
 
-def test_saturation_hazards_hover(gpu, oracle):
+def test_saturation_hazards_hover(gpu, oracle, engine):
     """a hovering drone next to a wall drives cells into both clamps with interleaved +6 / -1:
     the order-sensitive case of SURVEY 0.4 (accumulate-then-clamp gets these cells wrong)."""
     rng = np.random.default_rng(5)
@@ -198,7 +207,7 @@ def test_saturation_hazards_hover(gpu, oracle):
     assert (want == 80).sum() > 0 and (want == -80).sum() > 0
 
 
-def test_short_ranges_share_cells_inside_one_frame(gpu, oracle):
+def test_short_ranges_share_cells_inside_one_frame(gpu, oracle, engine):
     """ranges of a few cells: several beams of ONE frame end in / pass through the same cells."""
     rng = np.random.default_rng(9)
     n = 3000
@@ -212,7 +221,7 @@ def test_short_ranges_share_cells_inside_one_frame(gpu, oracle):
     assert np.array_equal(got[0], want), first_diff(got[0], want)
 
 
-def test_other_log_odds_constants(gpu, oracle, synth):
+def test_other_log_odds_constants(gpu, oracle, synth, engine):
     """LO_FREE_DEC=3 makes the max-range end cell rule -(3/2) = -1 (integer division, uav_local_nav.c:266)."""
     w = synth.scaled(synth.CONFIGS["c1"], n_samples=800)
     d = synth.generate(w)
@@ -243,6 +252,7 @@ def test_result_is_independent_of_subtile_size(gpu, oracle, synth):
     d = synth.generate(w)
     p = w.params()
     want, _ = oracle_grids(oracle, p, d)
+    gpu.set_engine(1, 0)
     try:
         for sw, sh in [(0, 0), (32, 32), (64, 48), (100, 100), (400, 20), (52, 200), (7, 13)]:
             gpu.set_tuning(sw, sh, 0)
@@ -250,6 +260,7 @@ def test_result_is_independent_of_subtile_size(gpu, oracle, synth):
             assert np.array_equal(got, want), ((sw, sh), first_diff(got, want))
     finally:
         gpu.set_tuning(0, 0, 0)
+        gpu.set_engine(0, 0)
 
 
 def test_chained_replays_and_row_bands_via_device_api(gpu, oracle, synth):

@@ -1,5 +1,6 @@
 """Scratch timing script for early GPU runs (replaced by bench.py)."""
-import importlib, time, sys
+import importlib, time, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 m = importlib.import_module("micro-quad-slam_b200"); syn = importlib.import_module("micro-quad-slam_b200.synth")
 m.init(0)
