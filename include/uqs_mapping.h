@@ -146,6 +146,10 @@ int uqs_replay(const uqs_params* p, int n_flights, int n_frames,
                const float* x, const float* y, const float* yaw_deg, const float* ranges,
                int8_t* grids_out, uqs_stats* stats);
 
+/* The host-buffer calls cut the flights into chunks and overlap H2D, kernels and D2H of
+ * successive chunks (page-locked host buffers needed for the overlap).  0 = automatic. */
+int uqs_set_host_chunk(int flights_per_chunk);
+
 /* Same, with every pointer a DEVICE pointer on the device given to uqs_init().
  * accumulate != 0 continues from the grids' current contents instead of zero
  * (used for chained replays and by the drop-in symbols).  row0/rows restrict

@@ -80,7 +80,7 @@ _EXPORTS = [
     # batch API
     "uqs_params_default", "uqs_init", "uqs_shutdown", "uqs_last_error", "uqs_device_sm_count",
     "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_kernel_launches",
-    "uqs_set_profiling", "uqs_profile_collect",
+    "uqs_set_profiling", "uqs_profile_collect", "uqs_set_host_chunk",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
     "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
     # drop-in symbols
@@ -165,6 +165,10 @@ def set_tuning(subtile_w: int = 0, subtile_h: int = 0, time_slices: int = 0):
 def set_engine(engine: int = 0, flight_warps: int = 0):
     """0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA (identical results)."""
     _check(lib().uqs_set_engine(engine, flight_warps))
+
+
+def set_host_chunk(flights: int = 0):
+    _check(lib().uqs_set_host_chunk(int(flights)))
 
 
 def set_profiling(on: bool):

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/uqs_mapping.h"
 #include "uqs_host.h"
@@ -136,9 +137,9 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   while (ring_size > 32 && (size_t)fpitch * dp.H + (size_t)ring_size * nw > kFlightSmemMax) ring_size >>= 1;
   const size_t fsmem = (size_t)fpitch * dp.H + (size_t)ring_size * nw;
   // auto: the frame-synchronous resident engine wins while flights are too few to fill the chip with
-  // independent sub-tile warps (measured crossover ~4 flights per SM); beyond that sub-tiles win
+  // independent sub-tile warps (measured crossover ~2 flights per SM); beyond that sub-tiles win
   const bool fits = row0 == 0 && rows == dp.H && fsmem <= kFlightSmemMax;
-  const bool resident = fits && (g_ctx.engine == 2 || (g_ctx.engine == 0 && n_flights <= 4 * g_ctx.sm_count));
+  const bool resident = fits && (g_ctx.engine == 2 || (g_ctx.engine == 0 && n_flights <= 2 * g_ctx.sm_count));
   if (g_ctx.engine == 2 && !fits) {
     set_error("engine 2 (grid resident per CTA) needs the whole %dx%d grid in %zu B of shared memory", dp.W, dp.H, kFlightSmemMax);
     return UQS_ERR_BAD_ARG;
@@ -154,11 +155,11 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   const size_t budget = g_ctx.scratch_budget;
   int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_flights, budget / std::max<size_t>(per_flight, 1)));
   int rc;
-  if ((rc = g_ctx.ws_rays.ensure((size_t)chunk * n_frames * 32 * sizeof(uint2)))) return rc;
-  if ((rc = g_ctx.ws_frames.ensure((size_t)chunk * n_frames * sizeof(uint4)))) return rc;
-  if ((rc = g_ctx.ws_groups.ensure((size_t)chunk * gpf * sizeof(uint2)))) return rc;
-  if ((rc = g_ctx.ws_counters.ensure(64 * sizeof(unsigned long long)))) return rc;
-  unsigned long long* counters = (unsigned long long*)g_ctx.ws_counters.p;   // [0..3] stats, [8+] job counters
+  if ((rc = g_ctx.w->rays.ensure((size_t)chunk * n_frames * 32 * sizeof(uint2)))) return rc;
+  if ((rc = g_ctx.w->frames.ensure((size_t)chunk * n_frames * sizeof(uint4)))) return rc;
+  if ((rc = g_ctx.w->groups.ensure((size_t)chunk * gpf * sizeof(uint2)))) return rc;
+  if ((rc = g_ctx.w->counters.ensure(64 * sizeof(unsigned long long)))) return rc;
+  unsigned long long* counters = (unsigned long long*)g_ctx.w->counters.p;   // [0..3] stats, [8+] job counters
   cudaError_t e;
   if (reset_stats) {
     e = cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), st);
@@ -182,16 +183,16 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     const size_t fo = (size_t)f0 * n_frames;
     KernelTimer t_setup(1);
     k_ray_setup<<<(unsigned)(nf * gpf), 1024, 0, st>>>(
-        dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr,
-        (uint4*)g_ctx.ws_frames.p, (uint2*)g_ctx.ws_groups.p, (uint2*)g_ctx.ws_rays.p, counters);
+        dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, resident ? 1 : 0,
+        (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
     e = cudaGetLastError();
     t_setup.stop();
     if (e != cudaSuccess) return cuda_fail(e, "k_ray_setup launch");
 
     if (resident) {
       FlightArgs FA;
-      FA.frames = (const uint4*)g_ctx.ws_frames.p;
-      FA.rays = (const uint2*)g_ctx.ws_rays.p;
+      FA.frames = (const uint4*)g_ctx.w->frames.p;
+      FA.rays = (const uint2*)g_ctx.w->rays.p;
       FA.grids = grids + (size_t)f0 * dp.W * dp.H;
       FA.job_counter = counters + 8;
       FA.n_flights = nf; FA.n_frames = n_frames;
@@ -209,10 +210,29 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       g_ctx.launches += 2;
       continue;
     }
+    // sub-tiles nearest the grid centre first (trajectories stay within 60 % of the half-extent,
+    // so those are the heavy ones); cached per geometry
+    if (g_ctx.w->order_nsx != nsx || g_ctx.w->order_nsy != nsy) {
+      std::vector<uint32_t> ord((size_t)nsx * nsy);
+      for (uint32_t i = 0; i < ord.size(); i++) ord[i] = i;
+      auto dist2 = [&](uint32_t t) {
+        const double cx = ((t % nsx) + 0.5) * sw - dp.W * 0.5, cy = ((t / nsx) + 0.5) * sh + row0 - dp.H * 0.5;
+        return cx * cx + cy * cy;
+      };
+      std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return dist2(a) < dist2(b); });
+      if ((rc = g_ctx.w->order.ensure(ord.size() * sizeof(uint32_t)))) return rc;
+      e = cudaMemcpyAsync(g_ctx.w->order.p, ord.data(), ord.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // ord is a local
+      if (e != cudaSuccess) return cuda_fail(e, "tile order upload");
+      g_ctx.w->order_nsx = nsx;
+      g_ctx.w->order_nsy = nsy;
+    }
     ReplayArgs A;
-    A.frames = (const uint4*)g_ctx.ws_frames.p;
-    A.groups = (const uint2*)g_ctx.ws_groups.p;
-    A.rays = (const uint2*)g_ctx.ws_rays.p;
+    A.tile_order = (const uint32_t*)g_ctx.w->order.p;
+    A.n_flights = nf;
+    A.frames = (const uint4*)g_ctx.w->frames.p;
+    A.groups = (const uint2*)g_ctx.w->groups.p;
+    A.rays = (const uint2*)g_ctx.w->rays.p;
     A.grids = grids + (size_t)f0 * dp.W * dp.H;
     A.job_counter = counters + 8;
     A.total_jobs = (unsigned long long)nf * nsx * nsy;
@@ -237,35 +257,47 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   return UQS_OK;
 }
 
-int fetch_stats(uqs_stats* stats, uint64_t frames) {
+// counters of every Work in `mask` (bit i = works[i]) summed; synchronises their streams
+int fetch_stats_mask(uqs_stats* stats, uint64_t frames, unsigned mask) {
   if (!stats) return UQS_OK;
-  unsigned long long h[4];
-  cudaError_t e = cudaMemcpyAsync(h, g_ctx.ws_counters.p, sizeof(h), cudaMemcpyDeviceToHost, g_ctx.stream());
-  if (e != cudaSuccess) return cuda_fail(e, "stats D2H");
-  e = cudaStreamSynchronize(g_ctx.stream());
-  if (e != cudaSuccess) return cuda_fail(e, "stats sync");
-  stats->ray_cell_updates = h[0];
-  stats->rays_accepted = h[1];
-  stats->rays_skipped = h[2];
-  stats->domain_errors = h[3];
+  unsigned long long tot[4] = { 0, 0, 0, 0 };
+  for (int i = 0; i < 3; i++) {
+    if (!(mask & (1u << i)) || !g_ctx.works[i].counters.p) continue;
+    Work* saved = g_ctx.w;
+    g_ctx.w = &g_ctx.works[i];
+    cudaStream_t st = g_ctx.stream();
+    g_ctx.w = saved;
+    unsigned long long h[4];
+    cudaError_t e = cudaMemcpyAsync(h, g_ctx.works[i].counters.p, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "stats D2H");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "stats sync");
+    for (int k = 0; k < 4; k++) tot[k] += h[k];
+  }
+  stats->ray_cell_updates = tot[0];
+  stats->rays_accepted = tot[1];
+  stats->rays_skipped = tot[2];
+  stats->domain_errors = tot[3];
   stats->frames = frames;
-  if (h[3]) {
-    set_error("%llu rays left the exact-arithmetic domain (|angle| >= 120 rad or > %d cells)", h[3], kMaxRayCells);
+  if (tot[3]) {
+    set_error("%llu rays left the exact-arithmetic domain (|angle| >= 120 rad or > %d cells)", tot[3], kMaxRayCells);
     return UQS_ERR_DOMAIN;
   }
   return UQS_OK;
 }
+
+int fetch_stats(uqs_stats* stats, uint64_t frames) { return fetch_stats_mask(stats, frames, 1u); }
 
 int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float* rx, const float* ry,
                 const float* h, const float* yaw, const uint8_t* q, float* xo, float* yo, int mode) {
   cudaStream_t st = g_ctx.stream();
   const long long total = (long long)n_flights * n_samples;
   int rc;
-  if ((rc = g_ctx.ws_inc.ensure((size_t)total * 2 * sizeof(float)))) return rc;
-  if ((rc = g_ctx.ws_counters.ensure(64 * sizeof(unsigned long long)))) return rc;
-  float* inc_n = (float*)g_ctx.ws_inc.p;
+  if ((rc = g_ctx.w->inc.ensure((size_t)total * 2 * sizeof(float)))) return rc;
+  if ((rc = g_ctx.w->counters.ensure(64 * sizeof(unsigned long long)))) return rc;
+  float* inc_n = (float*)g_ctx.w->inc.p;
   float* inc_e = inc_n + total;
-  unsigned long long* dom = (unsigned long long*)g_ctx.ws_counters.p + 16;
+  unsigned long long* dom = (unsigned long long*)g_ctx.w->counters.p + 16;
   cudaError_t e = cudaMemsetAsync(dom, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess) return cuda_fail(e, "memset pose counter");
   volatile float pi_f = (float)M_PI;
@@ -283,12 +315,12 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
     const int tile = pose_scan_tile();
     const int ppf = (n_samples + tile - 1) / tile;
     const size_t nparts = (size_t)n_flights * ppf;
-    if ((rc = g_ctx.ws_scan.ensure(nparts * pose_scan_state_bytes() + 64))) return rc;
-    e = cudaMemsetAsync(g_ctx.ws_scan.p, 0, nparts * pose_scan_state_bytes() + 64, st);
+    if ((rc = g_ctx.w->scan.ensure(nparts * pose_scan_state_bytes() + 64))) return rc;
+    e = cudaMemsetAsync(g_ctx.w->scan.p, 0, nparts * pose_scan_state_bytes() + 64, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset scan state");
-    unsigned int* ticket = (unsigned int*)((char*)g_ctx.ws_scan.p + nparts * pose_scan_state_bytes());
+    unsigned int* ticket = (unsigned int*)((char*)g_ctx.w->scan.p + nparts * pose_scan_state_bytes());
     k_pose_scan<<<(unsigned)nparts, pose_scan_threads(), 0, st>>>(n_flights, n_samples, ppf, inc_n, inc_e, xo, yo,
-                                                                  (volatile ScanState*)g_ctx.ws_scan.p, ticket);
+                                                                  (volatile ScanState*)g_ctx.w->scan.p, ticket);
   }
   e = cudaGetLastError();
   t_pose.stop();
@@ -350,6 +382,7 @@ void uqs_shutdown(void) {
   cudaSetDevice(g_ctx.device);
   cudaDeviceSynchronize();
   dropin_release();
+  pipeline_release();
   g_ctx.release_all();
   if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
   g_ctx.own_stream = nullptr;
@@ -493,73 +526,6 @@ int uqs_pose_integrate(int n_flights, int n_samples, const uint32_t* t_ms, const
   return UQS_OK;
 }
 
-static int replay_host_common(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames,
-                              const float* ranges, int8_t* grids_out, uqs_stats* stats) {
-  int rc;
-  const size_t n = (size_t)n_flights * n_frames;
-  const size_t gbytes = (size_t)n_flights * p->W * p->H;
-  if ((rc = h2d(g_ctx.in_ranges, ranges, n * 32 * 4, "ranges H2D"))) return rc;
-  if ((rc = g_ctx.out_grids.ensure(gbytes))) return rc;
-  if ((rc = replay_device(dp, n_flights, n_frames, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p, (float*)g_ctx.in_yaw.p,
-                          (float*)g_ctx.in_ranges.p, nullptr, (int8_t*)g_ctx.out_grids.p, 0, 0, p->H, true)))
-    return rc;
-  cudaError_t e = cudaMemcpyAsync(grids_out, g_ctx.out_grids.p, gbytes, cudaMemcpyDeviceToHost, g_ctx.stream());
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream());
-  if (e != cudaSuccess) return cuda_fail(e, "grids D2H");
-  uqs_stats local;
-  rc = fetch_stats(stats ? stats : &local, n);
-  return rc;
-}
-
-int uqs_replay(const uqs_params* p, int n_flights, int n_frames, const float* x, const float* y,
-               const float* yaw, const float* ranges, int8_t* grids_out, uqs_stats* stats) {
-  int rc = check_ready();
-  if (rc) return rc;
-  DevParams dp;
-  if ((rc = make_dev_params(p, &dp))) return rc;
-  if (n_flights <= 0 || n_frames <= 0 || !x || !y || !yaw || !ranges || !grids_out) {
-    set_error("uqs_replay: NULL pointer or non-positive size");
-    return UQS_ERR_BAD_ARG;
-  }
-  const size_t n = (size_t)n_flights * n_frames;
-  if ((rc = h2d(g_ctx.in_x, x, n * 4, "x H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_y, y, n * 4, "y H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D"))) return rc;
-  return replay_host_common(p, dp, n_flights, n_frames, ranges, grids_out, stats);
-}
-
-int uqs_replay_flow(const uqs_params* p, int n_flights, int n_samples, const uint32_t* t_ms,
-                    const float* rx, const float* ry, const float* h, const float* yaw,
-                    const uint8_t* q, const float* ranges, int8_t* grids_out, float* pox, float* poy,
-                    uqs_stats* stats) {
-  int rc = check_ready();
-  if (rc) return rc;
-  DevParams dp;
-  if ((rc = make_dev_params(p, &dp))) return rc;
-  if (n_flights <= 0 || n_samples <= 0 || !t_ms || !rx || !ry || !h || !yaw || !q || !ranges || !grids_out) {
-    set_error("uqs_replay_flow: NULL pointer or non-positive size");
-    return UQS_ERR_BAD_ARG;
-  }
-  const size_t n = (size_t)n_flights * n_samples;
-  if ((rc = h2d(g_ctx.in_t, t_ms, n * 4, "t_ms H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_rx, rx, n * 4, "of_rate_x H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_ry, ry, n * 4, "of_rate_y H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_h, h, n * 4, "h_m H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D"))) return rc;
-  if ((rc = h2d(g_ctx.in_q, q, n, "of_q H2D"))) return rc;
-  if ((rc = g_ctx.in_x.ensure(n * 4)) || (rc = g_ctx.in_y.ensure(n * 4))) return rc;
-  if ((rc = pose_device(n_flights, n_samples, (uint32_t*)g_ctx.in_t.p, (float*)g_ctx.in_rx.p, (float*)g_ctx.in_ry.p,
-                        (float*)g_ctx.in_h.p, (float*)g_ctx.in_yaw.p, (uint8_t*)g_ctx.in_q.p, (float*)g_ctx.in_x.p,
-                        (float*)g_ctx.in_y.p, 0)))
-    return rc;
-  if (pox && poy) {
-    cudaError_t e = cudaMemcpyAsync(pox, g_ctx.in_x.p, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream());
-    if (e == cudaSuccess) e = cudaMemcpyAsync(poy, g_ctx.in_y.p, n * 4, cudaMemcpyDeviceToHost, g_ctx.stream());
-    if (e != cudaSuccess) return cuda_fail(e, "pose D2H");
-  }
-  return replay_host_common(p, dp, n_flights, n_samples, ranges, grids_out, stats);
-}
-
 int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const float* y, const float* yaw,
                    const float* ranges, int32_t* cells_out, int32_t* origin_out) {
   int rc = check_ready();
@@ -573,20 +539,20 @@ int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const floa
   if ((rc = h2d(g_ctx.in_x, x, n * 4, "x H2D")) || (rc = h2d(g_ctx.in_y, y, n * 4, "y H2D")) ||
       (rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D")) || (rc = h2d(g_ctx.in_ranges, ranges, n * 128, "ranges H2D")))
     return rc;
-  if ((rc = g_ctx.ws_rays.ensure(n * 32 * sizeof(uint2))) || (rc = g_ctx.ws_frames.ensure(n * sizeof(uint4))) ||
-      (rc = g_ctx.ws_groups.ensure((size_t)gpf * sizeof(uint2))) || (rc = g_ctx.ws_counters.ensure(64 * 8)) ||
+  if ((rc = g_ctx.w->rays.ensure(n * 32 * sizeof(uint2))) || (rc = g_ctx.w->frames.ensure(n * sizeof(uint4))) ||
+      (rc = g_ctx.w->groups.ensure((size_t)gpf * sizeof(uint2))) || (rc = g_ctx.w->counters.ensure(64 * 8)) ||
       (rc = g_ctx.out_grids.ensure(n * 32 * 2 * 4 + n * 2 * 4)))
     return rc;
-  cudaError_t e = cudaMemsetAsync(g_ctx.ws_counters.p, 0, 64, st);
+  cudaError_t e = cudaMemsetAsync(g_ctx.w->counters.p, 0, 64, st);
   if (e != cudaSuccess) return cuda_fail(e, "memset");
   k_ray_setup<<<(unsigned)gpf, 1024, 0, st>>>(dp, n_frames, gpf, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p,
-                                              (float*)g_ctx.in_yaw.p, (float*)g_ctx.in_ranges.p, nullptr,
-                                              (uint4*)g_ctx.ws_frames.p, (uint2*)g_ctx.ws_groups.p,
-                                              (uint2*)g_ctx.ws_rays.p, (unsigned long long*)g_ctx.ws_counters.p);
+                                              (float*)g_ctx.in_yaw.p, (float*)g_ctx.in_ranges.p, nullptr, 0,
+                                              (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p,
+                                              (uint2*)g_ctx.w->rays.p, (unsigned long long*)g_ctx.w->counters.p);
   int32_t* d_cells = (int32_t*)g_ctx.out_grids.p;
   int32_t* d_origin = d_cells + n * 64;
-  k_records_to_cells<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>((long long)n, (uint4*)g_ctx.ws_frames.p,
-                                                                       (uint2*)g_ctx.ws_rays.p, d_cells, d_origin);
+  k_records_to_cells<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>((long long)n, (uint4*)g_ctx.w->frames.p,
+                                                                       (uint2*)g_ctx.w->rays.p, d_cells, d_origin);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "beam_cells kernels");
   e = cudaMemcpyAsync(cells_out, d_cells, n * 64 * 4, cudaMemcpyDeviceToHost, st);
@@ -626,14 +592,14 @@ int uqs_measure_rmw_peak(double* updates_per_s) {
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rmw_peak, kReplayThreads, smem);
   if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "occupancy(k_rmw_peak)");
-  if ((rc = g_ctx.ws_counters.ensure(64 * 8))) return rc;
+  if ((rc = g_ctx.w->counters.ensure(64 * 8))) return rc;
   const unsigned grid = (unsigned)(per_sm * g_ctx.sm_count);
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
-  k_rmw_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, 64, -80, (int*)g_ctx.ws_counters.p + 96);
+  k_rmw_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, 64, -80, (int*)g_ctx.w->counters.p + 96);
   cudaEventRecord(a, st);
-  k_rmw_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, iters, -80, (int*)g_ctx.ws_counters.p + 96);
+  k_rmw_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, iters, -80, (int*)g_ctx.w->counters.p + 96);
   cudaEventRecord(b, st);
   e = cudaEventSynchronize(b);
   float ms = 0.f;

@@ -18,6 +18,19 @@ struct DevBuf {
   void release();
 };
 
+// scratch of one in-flight replay: ray/frame records, counters, P0 increments (+ an optional
+// stream override, used by the host-buffer pipeline to keep two chunks' kernels in flight)
+struct Work {
+  DevBuf rays, frames, groups, counters, inc, scan, order;
+  int order_nsx = 0, order_nsy = 0;             // geometry the cached tile order was built for
+  cudaStream_t stream = nullptr;
+  void release() {
+    DevBuf* all[] = { &rays, &frames, &groups, &counters, &inc, &scan, &order };
+    order_nsx = order_nsy = 0;
+    for (DevBuf* b : all) b->release();
+  }
+};
+
 struct Context {
   bool ready = false;
   int device = -1;
@@ -28,10 +41,12 @@ struct Context {
   int tune_sw = 0, tune_sh = 0, tune_slices = 0;
   int engine = 0;                               // 0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA
   int flight_warps = 0;                         // warps per CTA of the resident engine (0 = 16)
+  int host_chunk = 0;                           // flights per chunk of the host-buffer pipeline (0 = auto)
   size_t scratch_budget = (size_t)12 << 30;     // ray/frame records held at once
   unsigned long long launches = 0;              // kernels launched by this library
-  // scratch
-  DevBuf ws_rays, ws_frames, ws_groups, ws_counters, ws_inc, ws_scan;
+  // scratch: works[0] serves the device-pointer API and the drop-in, works[1..2] the pipeline
+  Work works[3];
+  Work* w = &works[0];
   // staging for the host-buffer entry points
   DevBuf in_t, in_rx, in_ry, in_h, in_yaw, in_q, in_x, in_y, in_ranges, in_kind, out_grids;
 
@@ -40,11 +55,12 @@ struct Context {
   struct Span { cudaEvent_t a, b; int kind; };   // kind 0 pose, 1 ray set-up, 2 replay
   std::vector<Span> spans;
 
-  cudaStream_t stream() const { return use_ext ? ext_stream : own_stream; }
+  cudaStream_t stream() const { return w->stream ? w->stream : (use_ext ? ext_stream : own_stream); }
+  cudaStream_t user_stream() const { return use_ext ? ext_stream : own_stream; }
   void release_all() {
-    DevBuf* all[] = { &ws_rays, &ws_frames, &ws_groups, &ws_counters, &ws_inc, &ws_scan, &in_t, &in_rx,
-                      &in_ry, &in_h, &in_yaw, &in_q, &in_x, &in_y, &in_ranges, &in_kind, &out_grids };
+    DevBuf* all[] = { &in_t, &in_rx, &in_ry, &in_h, &in_yaw, &in_q, &in_x, &in_y, &in_ranges, &in_kind, &out_grids };
     for (DevBuf* b : all) b->release();
+    for (Work& k : works) k.release();
   }
 };
 
@@ -60,7 +76,11 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
                   const float* yaw, const float* ranges, const uint8_t* kind, int8_t* grids,
                   int accumulate, int row0, int rows, bool reset_stats);
 int fetch_stats(uqs_stats* stats, uint64_t frames);
+int fetch_stats_mask(uqs_stats* stats, uint64_t frames, unsigned mask);
 void dropin_release();
+void pipeline_release();
+int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float* rx, const float* ry,
+                const float* h, const float* yaw, const uint8_t* q, float* xo, float* yo, int mode);
 
 // RAII-free helper: records an event pair around a kernel launch when profiling is on
 struct KernelTimer {

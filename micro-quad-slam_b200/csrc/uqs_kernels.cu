@@ -189,7 +189,7 @@ size_t pose_scan_state_bytes() { return sizeof(ScanState); }
 __global__ void __launch_bounds__(1024)
 k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __restrict__ x,
             const float* __restrict__ y, const float* __restrict__ yaw_deg,
-            const float* __restrict__ ranges, const uint8_t* __restrict__ kind,
+            const float* __restrict__ ranges, const uint8_t* __restrict__ kind, int want_k0,
             uint4* __restrict__ frames, uint2* __restrict__ groups, uint2* __restrict__ rays,
             unsigned long long* __restrict__ stats /* [4]: U, accepted, skipped, domain */) {
   __shared__ int s_box[4][32];
@@ -251,7 +251,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
     // radius k, so beams i,j are apart for every k > 1/|sigma_i - sigma_j|.  Conservative
     // float arithmetic (K0 may only be too large) -- it gates a fast path, never a result.
     int k0 = 0;
-    {
+    if (want_k0) {                       // only the grid-resident engine reads K0
       const int dx = sext12(w0), dy = sext12(w0 >> 12);
       const int adx = abs(dx), ady = abs(dy);
       const bool xmaj = adx >= ady;
@@ -364,65 +364,75 @@ __device__ __forceinline__ bool box_overlaps(uint32_t xlohi, uint32_t ylohi, int
   return bx0 < X1 && bx1 >= X0 && by0 < Y1 && by1 >= Y0;
 }
 
+// floor(num / den) for 0 <= num < 2^22, 1 <= den <= 1024: one reciprocal multiply and a +-1 fix-up
+// (num is exact in binary32; the product is within 1 of the quotient).
+__device__ __forceinline__ int div_small(int num, int den) {
+  int q = (int)((float)num * __frcp_rn((float)den));
+  const int r = num - q * den;
+  q += (r >= den) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
+}
+
 // Apply, in beam order, the part of every ray of one frame that lies inside the warp's
-// sub-tile [X0,X1) x [Y0,Y1).  Lane b first clips beam b (closed-form Bresenham, see
-// cell k of a ray is major0 + k*s_major, minor0 + s_minor*floor((k*n+m/2)/m));
-// then the warp walks the surviving rays one by one with lanes along the ray.
+// sub-tile [X0,X1) x [Y0,Y1).
+//   1. lane b clips beam b EXACTLY: cell k of a ray is (major0 + k*s, minor0 + s'*q(k)) with
+//      q(k) = floor((k*n + m/2)/m) non-decreasing, so "inside the tile" is one interval
+//      [ka, kb] of k: the major axis gives it directly, the minor axis by inverting q:
+//        q(k) >= a  <=>  k >= ceil((a*m - m/2)/n),   q(k) <= b  <=>  k <= floor(((b+1)*m - m/2 - 1)/n)
+//      and packs what the cell loop needs into four words;
+//   2. the warp walks the surviving beams in order, lanes along the ray: the cells of one ray
+//      are distinct, so plain byte read-modify-writes are race-free and in reference order.
 __device__ __forceinline__ void apply_frame(const ReplayArgs& A, int8_t* tile, int lane, int gx0,
                                             int gy0, uint2 rec, int X0, int X1, int Y0, int Y1) {
-  // ---- clip beam `lane` against the sub-tile ---------------------------------------
-  int ka = 0, kb = -1;
+  uint32_t p1, p2, p3;      // n2 | m<<16 ; cK | cQ<<16 ; ka | kb<<11 | hit<<22
+  bool live;
   {
     const int dx = sext12(rec.x), dy = sext12(rec.x >> 12);
     const int adx = abs(dx), ady = abs(dy);
     const bool xmaj = adx >= ady;
-    const int m = xmaj ? adx : ady, n = xmaj ? ady : adx;
-    const int c0 = xmaj ? gx0 : gy0, sM = xmaj ? (dx >= 0 ? 1 : -1) : (dy >= 0 ? 1 : -1);
+    const int m = xmaj ? adx : ady, n = xmaj ? ady : adx, h = m >> 1;
+    const bool majpos = (xmaj ? dx : dy) >= 0, minpos = (xmaj ? dy : dx) >= 0;
+    const int c0 = xmaj ? gx0 : gy0, c1 = xmaj ? gy0 : gx0;
     const int A0 = xmaj ? X0 : Y0, A1 = xmaj ? X1 : Y1;
-    const int lo = (sM > 0) ? (A0 - c0) : (c0 - (A1 - 1));
-    const int hi = (sM > 0) ? (A1 - 1 - c0) : (c0 - A0);
-    ka = max(lo, 0);
-    kb = min(hi, m);
-    if (!(rec.x & kRayValid)) kb = -1;
-    if (ka <= kb) {
-      const int n2 = 2 * n, h2 = 2 * (m >> 1);
-      const int qa = minor_steps(ka, n2, h2, rec.y), qb = minor_steps(kb, n2, h2, rec.y);
-      const int c1 = xmaj ? gy0 : gx0, sN = xmaj ? (dy >= 0 ? 1 : -1) : (dx >= 0 ? 1 : -1);
-      const int ma = c1 + sN * qa, mb = c1 + sN * qb;
-      const int B0 = xmaj ? Y0 : X0, B1 = xmaj ? Y1 : X1;
-      if (max(ma, mb) < B0 || min(ma, mb) >= B1) kb = -1;
+    const int B0 = xmaj ? Y0 : X0, B1 = xmaj ? Y1 : X1;
+    int ka = max(majpos ? (A0 - c0) : (c0 - (A1 - 1)), 0);
+    int kb = min(majpos ? (A1 - 1 - c0) : (c0 - A0), m);
+    const int qlo = minpos ? (B0 - c1) : (c1 - (B1 - 1));
+    const int qhi = minpos ? (B1 - 1 - c1) : (c1 - B0);
+    live = (rec.x & kRayValid) != 0u && qhi >= 0 && qlo <= n;
+    if (qlo > 0 && qlo <= n) {                                   // n >= 1 here
+      const int num = qlo * m - h;                               // > 0 because qlo*m >= m > h
+      ka = max(ka, div_small(num + n - 1, n));
     }
+    if (qhi >= 0 && qhi < n) kb = min(kb, div_small((qhi + 1) * m - h - 1, n));
+    live = live && ka <= kb;
+    const int pitch = A.pitch;
+    const int cK = majpos ? (xmaj ? 1 : pitch) : (xmaj ? -1 : -pitch);
+    const int cQ = minpos ? (xmaj ? pitch : 1) : (xmaj ? -pitch : -1);
+    p1 = (uint32_t)(2 * n) | ((uint32_t)m << 16);
+    p2 = ((uint32_t)cK & 0xffffu) | ((uint32_t)cQ << 16);
+    p3 = (uint32_t)ka | ((uint32_t)kb << 11) | ((rec.x & kRayHit) ? (1u << 22) : 0u);
   }
-  unsigned active = __ballot_sync(0xffffffffu, ka <= kb);
-  const int tw = X1 - X0, th = Y1 - Y0;
-  const int bx = gx0 - X0, by = gy0 - Y0;
-  // ---- rays in beam order, lanes along the ray ------------------------------------------
+  unsigned active = __ballot_sync(0xffffffffu, live);
+  const int base = (gy0 - Y0) * A.pitch + (gx0 - X0);
   while (active) {
     const int b = __ffs(active) - 1;
     active &= active - 1;
-    const uint32_t w0 = __shfl_sync(0xffffffffu, rec.x, b);
     const uint32_t inv = __shfl_sync(0xffffffffu, rec.y, b);
-    const int k0 = __shfl_sync(0xffffffffu, ka, b);
-    const int k1 = __shfl_sync(0xffffffffu, kb, b);
-    const int dx = sext12(w0), dy = sext12(w0 >> 12);
-    const int adx = abs(dx), ady = abs(dy);
-    const bool xmaj = adx >= ady;
-    const int m = xmaj ? adx : ady, n = xmaj ? ady : adx;
-    const int n2 = 2 * n, h2 = 2 * (m >> 1);
-    const int sx = dx >= 0 ? 1 : -1, sy = dy >= 0 ? 1 : -1;
-    const int end_delta = (w0 & kRayHit) ? A.lo_occ : A.end_nohit;
-    for (int k = k0 + lane; k <= k1; k += 32) {
+    const uint32_t q1 = __shfl_sync(0xffffffffu, p1, b);
+    const uint32_t q2 = __shfl_sync(0xffffffffu, p2, b);
+    const uint32_t q3 = __shfl_sync(0xffffffffu, p3, b);
+    const int n2 = (int)(q1 & 0xffffu), m = (int)(q1 >> 16), h2 = m & ~1;
+    const int cK = (int)(short)(q2 & 0xffffu), cQ = (int)q2 >> 16;
+    const int k1 = (int)((q3 >> 11) & 0x7ffu);
+    const int end_delta = (q3 & (1u << 22)) ? A.lo_occ : A.end_nohit;
+    for (int k = (int)(q3 & 0x7ffu) + lane; k <= k1; k += 32) {
       const int q = minor_steps(k, n2, h2, inv);
-      const int lx = bx + sx * (xmaj ? k : q);
-      const int ly = by + sy * (xmaj ? q : k);
-      if ((unsigned)lx < (unsigned)tw && (unsigned)ly < (unsigned)th) {
-        int8_t* cell = tile + ly * A.pitch + lx;
-        const int delta = (k == m) ? end_delta : -A.lo_free;
-        int v = (int)*cell + delta;
-        v = max(v, A.lo_min);
-        v = min(v, A.lo_max);
-        *cell = (int8_t)v;
-      }
+      int8_t* cell = tile + (base + k * cK + q * cQ);
+      int v = (int)*cell + ((k == m) ? end_delta : -A.lo_free);
+      v = min(max(v, A.lo_min), A.lo_max);
+      *cell = (int8_t)v;
     }
     __syncwarp();
   }
@@ -442,8 +452,14 @@ k_replay_tiles(ReplayArgs A) {
     if (lane == 0) job = atomicAdd(A.job_counter, 1ull);
     job = __shfl_sync(0xffffffffu, job, 0);
     if (job >= A.total_jobs) break;
-    const int flight = (int)(job / subs_per_grid);
-    const int sub = (int)(job % subs_per_grid);
+    // job order: groups of kJobGroup flights; inside a group every flight's heaviest (most central)
+    // tile first -- the launch then ends on light tiles, and a group's records stay L2-resident
+    const unsigned long long per_group = (unsigned long long)kJobGroup * subs_per_grid;
+    const int grp = (int)(job / per_group);
+    const int in_grp = (int)(job - (unsigned long long)grp * per_group);
+    const int gsize = min(kJobGroup, A.n_flights - grp * kJobGroup);
+    const int flight = grp * kJobGroup + in_grp % gsize;
+    const int sub = A.tile_order ? (int)A.tile_order[in_grp / gsize] : in_grp / gsize;
     const int X0 = (sub % A.nsx) * A.sw, Y0 = A.row0 + (sub / A.nsx) * A.sh;
     const int X1 = min(X0 + A.sw, A.W), Y1 = min(Y0 + A.sh, A.row0 + A.rows);
     const int tw = X1 - X0, th = Y1 - Y0;

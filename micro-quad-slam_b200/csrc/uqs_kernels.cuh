@@ -6,6 +6,7 @@ namespace uqs {
 
 constexpr int kReplayThreads = 256;               // 8 warps per CTA, each owning one sub-tile
 constexpr int kReplayWarps = kReplayThreads / 32;
+constexpr int kJobGroup = 64;                     // flights per scheduling group of the sub-tile engine
 
 struct ReplayArgs {
   const uint4* frames;      // [n_flights][n_frames]
@@ -13,8 +14,9 @@ struct ReplayArgs {
   const uint2* rays;        // [n_flights][n_frames][32]
   int8_t* grids;            // [n_flights][H][W]
   unsigned long long* job_counter;
+  const uint32_t* tile_order;  // [nsx*nsy] sub-tile ids, heaviest first (nullptr = natural order)
   unsigned long long total_jobs;
-  int n_frames, groups_per_flight;
+  int n_flights, n_frames, groups_per_flight;
   int W, H;
   int row0, rows;           // rows of the grid this launch owns
   int sw, sh, nsx, nsy;     // sub-tile size and count per grid
@@ -53,7 +55,7 @@ int pose_scan_threads();
 
 __global__ void k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* x,
                             const float* y, const float* yaw_deg, const float* ranges,
-                            const uint8_t* kind, uint4* frames, uint2* groups, uint2* rays,
+                            const uint8_t* kind, int want_k0, uint4* frames, uint2* groups, uint2* rays,
                             unsigned long long* stats);
 __global__ void k_records_to_cells(long long n_frames, const uint4* frames, const uint2* rays,
                                    int32_t* cells, int32_t* origin);

@@ -300,6 +300,27 @@ def test_chained_replays_and_row_bands_via_device_api(gpu, oracle, synth):
         gpu.set_stream(None)
 
 
+def test_host_pipeline_chunking_does_not_change_results(gpu, oracle, synth):
+    """uqs_replay / uqs_replay_flow overlap H2D, kernels and D2H over chunks of flights: any chunk size
+    (incl. a ragged last chunk) must give the same grids, poses and update count."""
+    w = synth.scaled(synth.CONFIGS["c3"], n_flights=11, n_samples=500)
+    d = synth.generate(w)
+    p = w.params()
+    args = (d["t_ms"], d["of_rate_x"], d["of_rate_y"], d["h_m"], d["yaw_deg"], d["of_q"])
+    ox, oy = oracle.pose_integrate(*args)
+    want, U = oracle_grids(oracle, p, d, ox, oy)
+    try:
+        for chunk in (0, 1, 3, 4, 11, 64):
+            gpu.set_host_chunk(chunk)
+            grids, px, py, st = gpu.replay_flow(p, *args, d["ranges"])
+            assert np.array_equal(grids, want), (chunk, first_diff(grids, want))
+            assert np.array_equal(px.view(np.uint32), ox.view(np.uint32)) and st["ray_cell_updates"] == U
+            g2, st2 = gpu.replay(p, ox, oy, d["frame_yaw_deg"], d["ranges"])
+            assert np.array_equal(g2, want) and st2["ray_cell_updates"] == U
+    finally:
+        gpu.set_host_chunk(0)
+
+
 # ----------------------------------------------------------------------------------------------
 # P0
 # ----------------------------------------------------------------------------------------------
