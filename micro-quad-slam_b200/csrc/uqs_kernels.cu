@@ -364,6 +364,23 @@ __device__ __forceinline__ bool box_overlaps(uint32_t xlohi, uint32_t ylohi, int
   return bx0 < X1 && bx1 >= X0 && by0 < Y1 && by1 >= Y0;
 }
 
+// shared-memory byte access through 32-bit shared addresses (no generic->shared conversion per use)
+__device__ __forceinline__ int lds_s8(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, int v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// pin a kernel parameter in a register (otherwise it is re-read from the constant bank in inner loops)
+__device__ __forceinline__ int in_reg(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+
+struct TileConsts { int pitch, lo_free, lo_occ, lo_min, lo_max, end_nohit; };
+
 // floor(num / den) for 0 <= num < 2^22, 1 <= den <= 1024: one reciprocal multiply and a +-1 fix-up
 // (num is exact in binary32; the product is within 1 of the quotient).
 __device__ __forceinline__ int div_small(int num, int den) {
@@ -383,7 +400,7 @@ __device__ __forceinline__ int div_small(int num, int den) {
 //      and packs what the cell loop needs into four words;
 //   2. the warp walks the surviving beams in order, lanes along the ray: the cells of one ray
 //      are distinct, so plain byte read-modify-writes are race-free and in reference order.
-__device__ __forceinline__ void apply_frame(const ReplayArgs& A, int8_t* tile, int lane, int gx0,
+__device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, int lane, int gx0,
                                             int gy0, uint2 rec, int X0, int X1, int Y0, int Y1) {
   uint32_t p1, p2, p3;      // n2 | m<<16 ; cK | cQ<<16 ; ka | kb<<11 | hit<<22
   bool live;
@@ -415,7 +432,7 @@ __device__ __forceinline__ void apply_frame(const ReplayArgs& A, int8_t* tile, i
     p3 = (uint32_t)ka | ((uint32_t)kb << 11) | ((rec.x & kRayHit) ? (1u << 22) : 0u);
   }
   unsigned active = __ballot_sync(0xffffffffu, live);
-  const int base = (gy0 - Y0) * A.pitch + (gx0 - X0);
+  const uint32_t base = tile + (uint32_t)((gy0 - Y0) * A.pitch + (gx0 - X0));
   while (active) {
     const int b = __ffs(active) - 1;
     active &= active - 1;
@@ -429,10 +446,10 @@ __device__ __forceinline__ void apply_frame(const ReplayArgs& A, int8_t* tile, i
     const int end_delta = (q3 & (1u << 22)) ? A.lo_occ : A.end_nohit;
     for (int k = (int)(q3 & 0x7ffu) + lane; k <= k1; k += 32) {
       const int q = minor_steps(k, n2, h2, inv);
-      int8_t* cell = tile + (base + k * cK + q * cQ);
-      int v = (int)*cell + ((k == m) ? end_delta : -A.lo_free);
+      const uint32_t cell = base + (uint32_t)(k * cK + q * cQ);
+      int v = lds_s8(cell) + ((k == m) ? end_delta : -A.lo_free);
       v = min(max(v, A.lo_min), A.lo_max);
-      *cell = (int8_t)v;
+      sts_u8(cell, v);
     }
     __syncwarp();
   }
@@ -445,6 +462,9 @@ k_replay_tiles(ReplayArgs A) {
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   int8_t* tile = reinterpret_cast<int8_t*>(uqs_smem) + (size_t)wic * A.tile_bytes;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  const TileConsts C = { in_reg(A.pitch), in_reg(A.lo_free), in_reg(A.lo_occ), in_reg(A.lo_min), in_reg(A.lo_max),
+                         in_reg(A.end_nohit) };
   const int subs_per_grid = A.nsx * A.nsy;
 
   for (;;) {
@@ -514,7 +534,7 @@ k_replay_tiles(ReplayArgs A) {
           if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
           const int gx0 = (int)(__shfl_sync(0xffffffffu, fr.x, fi) & 0xffffu);
           const int gy0 = (int)(__shfl_sync(0xffffffffu, fr.y, fi) & 0xffffu);
-          apply_frame(A, tile, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
+          apply_frame(C, tile_s, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
         }
       }
     }
