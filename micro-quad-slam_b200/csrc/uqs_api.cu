@@ -99,13 +99,13 @@ int make_dev_params(const uqs_params* p, DevParams* d) {
   return UQS_OK;
 }
 
-// sub-tile geometry for a grid of W columns and `rows` owned rows
-static void choose_tiles(int W, int rows, int* sw, int* sh, int* nsx, int* nsy) {
-  auto pick = [](int extent, int forced, int* size, int* count) {
+// sub-tile geometry for a grid of W columns and `rows` owned rows, aiming at `target`-cell sub-tiles
+static void choose_tiles(int W, int rows, int target, int* sw, int* sh, int* nsx, int* nsy) {
+  auto pick = [target](int extent, int forced, int* size, int* count) {
     if (forced > 0) {
       *size = std::min(forced, extent);
     } else {
-      int n = std::max(1, (extent + 40) / 80);        // aim at ~80-cell sub-tiles
+      int n = std::max(1, (extent + target / 2) / target);
       int s = (extent + n - 1) / n;
       s = (s + 3) & ~3;
       *size = std::min(s, extent);
@@ -121,11 +121,39 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
                   int accumulate, int row0, int rows, bool reset_stats) {
   cudaStream_t st = g_ctx.stream();
   const int gpf = (n_frames + 31) / 32;
-  int sw, sh, nsx, nsy;
-  choose_tiles(dp.W, rows, &sw, &sh, &nsx, &nsy);
+  // Sub-tile engine geometry.  With plenty of (flight, tile) jobs, ~80-cell tiles and no time slicing.
+  // With few (one long log, one small flight) the chip would idle: cut the log into S time slices,
+  // replayed concurrently as clamp-add maps on 40-cell tiles and composed afterwards (exact).
+  int sw, sh, nsx, nsy, slices = 1;
+  choose_tiles(dp.W, rows, 80, &sw, &sh, &nsx, &nsy);
+  {
+    const long long warp_slots = (long long)g_ctx.sm_count * 32;
+    const long long jobs80 = (long long)n_flights * nsx * nsy;
+    int want = g_ctx.tune_slices;
+    if (want == 0 && jobs80 < 2 * warp_slots) {
+      int sw4, sh4, nx4, ny4;
+      choose_tiles(dp.W, rows, 40, &sw4, &sh4, &nx4, &ny4);
+      const long long jobs40 = (long long)n_flights * nx4 * ny4;
+      want = (int)std::min<long long>(64, std::max<long long>(1, 16 * warp_slots / std::max<long long>(jobs40, 1)));
+      want = std::min(want, std::max(1, gpf / 8));                  // at least 256 frames per slice
+    }
+    if (want > 1) {
+      const size_t map_bytes = (size_t)dp.W * dp.H * 4;
+      const size_t cap = ((size_t)6 << 30) / map_bytes;              // bound the map scratch
+      want = (int)std::min<size_t>((size_t)want, std::max<size_t>(cap, 1) + 1);
+    }
+    if (want > 1) {
+      slices = want;
+      choose_tiles(dp.W, rows, 40, &sw, &sh, &nsx, &nsy);
+    }
+  }
   int pitch = (sw + 3) & ~3;
   if (((pitch >> 2) & 1) == 0) pitch += 4;            // odd word pitch: column walks hit 32 banks
-  const int tile_bytes = pitch * sh;
+  const int pitch_cells = sw | 1;
+  if (slices > 1 && g_ctx.tune_slices == 0 && (size_t)pitch_cells * sh * 4 * kReplayWarps > 227u * 1024u)
+    slices = 1;                                        // a forced large sub-tile leaves no room for 32-bit map cells
+  const int gps = (gpf + slices - 1) / slices;          // 32-frame groups per slice
+  const int tile_bytes = slices > 1 ? std::max(pitch * sh, pitch_cells * sh * 4) : pitch * sh;
   size_t smem = (size_t)tile_bytes * kReplayWarps;
 
   // engine: whole grid resident in one CTA's shared memory (frame-synchronous) when it fits
@@ -136,10 +164,10 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   int ring_size = 256;                                    // per-warp collision table (power of two)
   while (ring_size > 32 && (size_t)fpitch * dp.H + (size_t)ring_size * nw > kFlightSmemMax) ring_size >>= 1;
   const size_t fsmem = (size_t)fpitch * dp.H + (size_t)ring_size * nw;
-  // auto: the frame-synchronous resident engine wins while flights are too few to fill the chip with
-  // independent sub-tile warps (measured crossover ~2 flights per SM); beyond that sub-tiles win
+  // auto: the frame-synchronous resident engine wins only in a narrow window of ~0.75..2 flights per SM
+  // (measured): below it the time-sliced sub-tile engine fills the chip better, above it plain sub-tiles do
   const bool fits = row0 == 0 && rows == dp.H && fsmem <= kFlightSmemMax;
-  const bool resident = fits && (g_ctx.engine == 2 || (g_ctx.engine == 0 && n_flights <= 2 * g_ctx.sm_count));
+  const bool resident = fits && (g_ctx.engine == 2 || (g_ctx.engine == 0 && 4 * n_flights >= 3 * g_ctx.sm_count && n_flights <= 2 * g_ctx.sm_count));
   if (g_ctx.engine == 2 && !fits) {
     set_error("engine 2 (grid resident per CTA) needs the whole %dx%d grid in %zu B of shared memory", dp.W, dp.H, kFlightSmemMax);
     return UQS_ERR_BAD_ARG;
@@ -235,7 +263,13 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     A.rays = (const uint2*)g_ctx.w->rays.p;
     A.grids = grids + (size_t)f0 * dp.W * dp.H;
     A.job_counter = counters + 8;
-    A.total_jobs = (unsigned long long)nf * nsx * nsy;
+    A.total_jobs = (unsigned long long)nf * nsx * nsy * slices;
+    A.slices = slices; A.groups_per_slice = gps; A.pitch_cells = pitch_cells;
+    A.maps = nullptr;
+    if (slices > 1) {
+      if ((rc = g_ctx.w->maps.ensure((size_t)nf * (slices - 1) * dp.W * dp.H * sizeof(uint32_t)))) return rc;
+      A.maps = (uint32_t*)g_ctx.w->maps.p;
+    }
     A.n_frames = n_frames; A.groups_per_flight = gpf;
     A.W = dp.W; A.H = dp.H; A.row0 = row0; A.rows = rows;
     A.sw = sw; A.sh = sh; A.nsx = nsx; A.nsy = nsy;
@@ -250,6 +284,12 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     KernelTimer t_rep(2);
     k_replay_tiles<<<grid, kReplayThreads, smem, st>>>(A);
     e = cudaGetLastError();
+    if (e == cudaSuccess && slices > 1) {
+      const size_t cells = (size_t)dp.W * rows * nf;
+      k_compose_slices<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(A.grids, A.maps, nf, dp.W, dp.H, slices, row0, rows);
+      e = cudaGetLastError();
+      g_ctx.launches += 1;
+    }
     t_rep.stop();
     if (e != cudaSuccess) return cuda_fail(e, "k_replay_tiles launch");
     g_ctx.launches += 2;

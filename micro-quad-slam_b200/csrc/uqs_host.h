@@ -21,11 +21,11 @@ struct DevBuf {
 // scratch of one in-flight replay: ray/frame records, counters, P0 increments (+ an optional
 // stream override, used by the host-buffer pipeline to keep two chunks' kernels in flight)
 struct Work {
-  DevBuf rays, frames, groups, counters, inc, scan, order;
+  DevBuf rays, frames, groups, counters, inc, scan, order, maps;
   int order_nsx = 0, order_nsy = 0;             // geometry the cached tile order was built for
   cudaStream_t stream = nullptr;
   void release() {
-    DevBuf* all[] = { &rays, &frames, &groups, &counters, &inc, &scan, &order };
+    DevBuf* all[] = { &rays, &frames, &groups, &counters, &inc, &scan, &order, &maps };
     order_nsx = order_nsy = 0;
     for (DevBuf* b : all) b->release();
   }

@@ -373,6 +373,14 @@ __device__ __forceinline__ int lds_s8(uint32_t a) {
 __device__ __forceinline__ void sts_u8(uint32_t a, int v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 // pin a kernel parameter in a register (otherwise it is re-read from the constant bank in inner loops)
 __device__ __forceinline__ int in_reg(int v) {
   asm volatile("" : "+r"(v));
@@ -400,6 +408,15 @@ __device__ __forceinline__ int div_small(int num, int den) {
 //      and packs what the cell loop needs into four words;
 //   2. the warp walks the surviving beams in order, lanes along the ray: the cells of one ray
 //      are distinct, so plain byte read-modify-writes are race-free and in reference order.
+//
+// MAP = false: the tile holds int8 log-odds values (the log, or its first time slice, from a known start).
+// MAP = true : the tile holds, per cell, the clamp-add MAP of a later time slice -- the function
+//   x -> value after the slice's updates when the cell starts at x -- as 32 bits
+//   [ a:16 | f(lo_max):8 | f(lo_min):8 ],  f(x) = min(max(x + a, f(lo_min)), f(lo_max)).
+//   The two end values are ordinary saturating trajectories; a (plain sum of the deltas, saturated far
+//   outside +-(lo_max-lo_min)) only matters while f(lo_min) < f(lo_max), and then it never saturated
+//   ("time slices").  k_compose_slices applies the maps in slice order.
+template <bool MAP>
 __device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, int lane, int gx0,
                                             int gy0, uint2 rec, int X0, int X1, int Y0, int Y1) {
   uint32_t p1, p2, p3;      // n2 | m<<16 ; cK | cQ<<16 ; ka | kb<<11 | hit<<22
@@ -432,7 +449,7 @@ __device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, 
     p3 = (uint32_t)ka | ((uint32_t)kb << 11) | ((rec.x & kRayHit) ? (1u << 22) : 0u);
   }
   unsigned active = __ballot_sync(0xffffffffu, live);
-  const uint32_t base = tile + (uint32_t)((gy0 - Y0) * A.pitch + (gx0 - X0));
+  const uint32_t base = tile + ((uint32_t)((gy0 - Y0) * A.pitch + (gx0 - X0)) << (MAP ? 2 : 0));
   while (active) {
     const int b = __ffs(active) - 1;
     active &= active - 1;
@@ -446,10 +463,20 @@ __device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, 
     const int end_delta = (q3 & (1u << 22)) ? A.lo_occ : A.end_nohit;
     for (int k = (int)(q3 & 0x7ffu) + lane; k <= k1; k += 32) {
       const int q = minor_steps(k, n2, h2, inv);
-      const uint32_t cell = base + (uint32_t)(k * cK + q * cQ);
-      int v = lds_s8(cell) + ((k == m) ? end_delta : -A.lo_free);
-      v = min(max(v, A.lo_min), A.lo_max);
-      sts_u8(cell, v);
+      const int delta = (k == m) ? end_delta : -A.lo_free;
+      if (!MAP) {
+        const uint32_t cell = base + (uint32_t)(k * cK + q * cQ);
+        const int v = lds_s8(cell) + delta;
+        sts_u8(cell, min(max(v, A.lo_min), A.lo_max));
+      } else {
+        const uint32_t cell = base + ((uint32_t)(k * cK + q * cQ) << 2);
+        const uint32_t w = lds_u32(cell);
+        int flo = (int)(int8_t)(w & 0xffu), fhi = (int)(int8_t)((w >> 8) & 0xffu), a = (int)w >> 16;
+        flo = min(max(flo + delta, A.lo_min), A.lo_max);
+        fhi = min(max(fhi + delta, A.lo_min), A.lo_max);
+        a = min(max(a + delta, -30000), 30000);
+        sts_u32(cell, ((uint32_t)flo & 0xffu) | (((uint32_t)fhi & 0xffu) << 8) | ((uint32_t)a << 16));
+      }
     }
     __syncwarp();
   }
@@ -463,9 +490,11 @@ k_replay_tiles(ReplayArgs A) {
   const int wic = threadIdx.x >> 5;
   int8_t* tile = reinterpret_cast<int8_t*>(uqs_smem) + (size_t)wic * A.tile_bytes;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-  const TileConsts C = { in_reg(A.pitch), in_reg(A.lo_free), in_reg(A.lo_occ), in_reg(A.lo_min), in_reg(A.lo_max),
-                         in_reg(A.end_nohit) };
+  const int lo_free = in_reg(A.lo_free), lo_occ = in_reg(A.lo_occ), lo_min = in_reg(A.lo_min), lo_max = in_reg(A.lo_max);
+  const TileConsts CV = { in_reg(A.pitch), lo_free, lo_occ, lo_min, lo_max, in_reg(A.end_nohit) };     // value tiles
+  const TileConsts CM = { in_reg(A.pitch_cells), lo_free, lo_occ, lo_min, lo_max, CV.end_nohit };       // map tiles
   const int subs_per_grid = A.nsx * A.nsy;
+  const int S = A.slices;
 
   for (;;) {
     unsigned long long job = 0;
@@ -473,21 +502,28 @@ k_replay_tiles(ReplayArgs A) {
     job = __shfl_sync(0xffffffffu, job, 0);
     if (job >= A.total_jobs) break;
     // job order: groups of kJobGroup flights; inside a group every flight's heaviest (most central)
-    // tile first -- the launch then ends on light tiles, and a group's records stay L2-resident
-    const unsigned long long per_group = (unsigned long long)kJobGroup * subs_per_grid;
+    // tile first -- the launch then ends on light tiles, and a group's records stay L2-resident;
+    // the S time slices of a (flight, tile) are separate jobs
+    const unsigned long long per_group = (unsigned long long)kJobGroup * subs_per_grid * S;
     const int grp = (int)(job / per_group);
     const int in_grp = (int)(job - (unsigned long long)grp * per_group);
     const int gsize = min(kJobGroup, A.n_flights - grp * kJobGroup);
     const int flight = grp * kJobGroup + in_grp % gsize;
-    const int sub = A.tile_order ? (int)A.tile_order[in_grp / gsize] : in_grp / gsize;
+    const int rank = in_grp / gsize;
+    const int slice = rank % S;
+    const int sub = A.tile_order ? (int)A.tile_order[rank / S] : rank / S;
     const int X0 = (sub % A.nsx) * A.sw, Y0 = A.row0 + (sub / A.nsx) * A.sh;
     const int X1 = min(X0 + A.sw, A.W), Y1 = min(Y0 + A.sh, A.row0 + A.rows);
     const int tw = X1 - X0, th = Y1 - Y0;
     int8_t* grid = A.grids + (size_t)flight * A.W * A.H;
     const bool vec = ((A.W | X0 | tw) & 3) == 0 && ((reinterpret_cast<size_t>(grid) & 3) == 0);
+    const bool map = slice > 0;
 
-    // ---- load (accumulate) or clear the sub-tile --------------------------------------
-    if (A.accumulate) {
+    // ---- start state: the grid (accumulate), zeros, or the identity map -----------------
+    if (map) {
+      const uint32_t ident = ((uint32_t)lo_min & 0xffu) | (((uint32_t)lo_max & 0xffu) << 8);
+      for (int i = lane; i < A.pitch_cells * th; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = ident;
+    } else if (A.accumulate) {
       if (vec) {
         const int wpr = tw >> 2;
         for (int i = lane; i < wpr * th; i += 32) {
@@ -506,13 +542,15 @@ k_replay_tiles(ReplayArgs A) {
     }
     __syncwarp();
 
-    // ---- walk the log in order, culling by group and frame bounding boxes -------------
+    // ---- walk the slice's frames in order, culling by group and frame bounding boxes ------
     const uint2* groups = A.groups + (size_t)flight * A.groups_per_flight;
     const uint4* frames = A.frames + (size_t)flight * A.n_frames;
     const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
-    for (int g0 = 0; g0 < A.groups_per_flight; g0 += 32) {
+    const int g_begin = slice * A.groups_per_slice;
+    const int g_end = min(g_begin + A.groups_per_slice, A.groups_per_flight);
+    for (int g0 = g_begin; g0 < g_end; g0 += 32) {
       bool ghit = false;
-      if (g0 + lane < A.groups_per_flight) {
+      if (g0 + lane < g_end) {
         const uint2 gb = __ldg(&groups[g0 + lane]);
         ghit = box_overlaps(gb.x, gb.y, X0, X1, Y0, Y1);
       }
@@ -534,14 +572,21 @@ k_replay_tiles(ReplayArgs A) {
           if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
           const int gx0 = (int)(__shfl_sync(0xffffffffu, fr.x, fi) & 0xffffu);
           const int gy0 = (int)(__shfl_sync(0xffffffffu, fr.y, fi) & 0xffffu);
-          apply_frame(C, tile_s, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
+          if (map) apply_frame<true>(CM, tile_s, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
+          else     apply_frame<false>(CV, tile_s, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
         }
       }
     }
     __syncwarp();
 
-    // ---- write the sub-tile back --------------------------------------------------------
-    if (vec) {
+    // ---- write the sub-tile back: values into the grid, maps into the slice scratch ---------
+    if (map) {
+      uint32_t* out = A.maps + ((size_t)flight * (S - 1) + (slice - 1)) * A.W * A.H;
+      for (int i = lane; i < tw * th; i += 32) {
+        const int r = i / tw, c = i - r * tw;
+        out[(size_t)(Y0 + r) * A.W + X0 + c] = reinterpret_cast<const uint32_t*>(tile)[r * A.pitch_cells + c];
+      }
+    } else if (vec) {
       const int wpr = tw >> 2;
       for (int i = lane; i < wpr * th; i += 32) {
         const int r = i / wpr, c = i - r * wpr;
@@ -556,6 +601,25 @@ k_replay_tiles(ReplayArgs A) {
     }
     __syncwarp();
   }
+}
+
+// Apply the slice maps 1..S-1, in order, to the value grid left by slice 0 (rows [row0, row0+rows)).
+__global__ void k_compose_slices(int8_t* __restrict__ grids, const uint32_t* __restrict__ maps, int n_flights,
+                                 int W, int H, int S, int row0, int rows) {
+  const size_t per = (size_t)W * rows;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per * n_flights) return;
+  const int flight = (int)(i / per);
+  const size_t cell = (size_t)row0 * W + (i - (size_t)flight * per);
+  int8_t* g = grids + (size_t)flight * W * H + cell;
+  int v = (int)*g;
+  const uint32_t* m = maps + (size_t)flight * (S - 1) * W * H + cell;
+  for (int s = 1; s < S; s++, m += (size_t)W * H) {
+    const uint32_t w = __ldg(m);
+    const int flo = (int)(int8_t)(w & 0xffu), fhi = (int)(int8_t)((w >> 8) & 0xffu), a = (int)w >> 16;
+    v = min(max(v + a, flo), fhi);
+  }
+  *g = (int8_t)v;
 }
 
 // ===========================================================================

@@ -21,6 +21,10 @@ struct ReplayArgs {
   int row0, rows;           // rows of the grid this launch owns
   int sw, sh, nsx, nsy;     // sub-tile size and count per grid
   int pitch, tile_bytes;    // shared-memory row pitch (bytes, odd number of words) and tile size
+  int pitch_cells;          // row pitch, in 32-bit cells, of a time-slice MAP tile (odd)
+  int slices;               // time slices per log (1 = none); slice s > 0 produces clamp-add maps
+  int groups_per_slice;     // 32-frame groups per slice
+  uint32_t* maps;           // [n_flights][slices-1][H][W] maps of slices 1..S-1
   int lo_free, lo_occ, lo_min, lo_max, end_nohit;
   int accumulate;
 };
@@ -62,6 +66,8 @@ __global__ void k_records_to_cells(long long n_frames, const uint4* frames, cons
 __global__ void k_sincosf(size_t n, const float* a, float* s, float* c);
 __global__ void k_world_to_grid_one(DevParams p, float wx, float wy, int* out);
 __global__ void k_replay_tiles(ReplayArgs A);
+__global__ void k_compose_slices(int8_t* grids, const uint32_t* maps, int n_flights, int W, int H, int S, int row0,
+                                 int rows);
 cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm);
 cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);

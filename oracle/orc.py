@@ -56,6 +56,8 @@ class Oracle:
         L.orc_magic_division_check.restype = C.c_long
         L.orc_clamp_monoid_check.restype = C.c_long
         L.orc_clamp_monoid_check.argtypes = [C.c_long, C.c_uint64]
+        L.orc_slice_map_check.restype = C.c_long
+        L.orc_slice_map_check.argtypes = [C.c_long, C.c_uint64]
         L.orc_fnv1a32.restype = C.c_uint32
         L.orc_fnv1a32.argtypes = [C.c_void_p, C.c_size_t]
 

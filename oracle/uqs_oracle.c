@@ -385,6 +385,48 @@ long orc_clamp_monoid_check(long n_seq, uint64_t seed) {
   return bad;
 }
 
+/* Time-slice map used by the sub-tile kernel: a slice's effect on a cell is kept as
+ * (f(lo_min), f(lo_max), a) with a the plain sum of deltas saturated at +-30000, and applied as
+ * f(x) = min(max(x + a, f(lo_min)), f(lo_max)).  Random op sequences (incl. very long ones, so that
+ * a saturates), every start value, and a two-slice composition; returns the number of mismatches. */
+long orc_slice_map_check(long n_seq, uint64_t seed) {
+  long bad = 0;
+  uint64_t s = seed ? seed : 0x9E3779B97F4A7C15ull;
+  for (long it = 0; it < n_seq; it++) {
+    int lens[2];
+    for (int h = 0; h < 2; h++) {
+      s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+      lens[h] = (s & 7) == 0 ? (int)(s % 70000) : (int)(s % 300);
+    }
+    int flo[2], fhi[2], a[2];
+    static int8_t ops[2][70000];
+    for (int h = 0; h < 2; h++) {
+      flo[h] = -80; fhi[h] = 80; a[h] = 0;
+      for (int i = 0; i < lens[h]; i++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        const int d = (s % 10) < 8 ? -1 : ((s % 10) == 8 ? 6 : 0);
+        ops[h][i] = (int8_t)d;
+        flo[h] = clampi(flo[h] + d, -80, 80);
+        fhi[h] = clampi(fhi[h] + d, -80, 80);
+        a[h] = clampi(a[h] + d, -30000, 30000);
+      }
+    }
+    for (int x0 = -80; x0 <= 80; x0++) {
+      int v = x0;
+      for (int h = 0; h < 2; h++)
+        for (int i = 0; i < lens[h]; i++) v = clampi(v + ops[h][i], -80, 80);
+      int w = x0;
+      for (int h = 0; h < 2; h++) {
+        w = w + a[h];
+        if (w < flo[h]) w = flo[h];
+        if (w > fhi[h]) w = fhi[h];
+      }
+      if (w != v) bad++;
+    }
+  }
+  return bad;
+}
+
 /* FNV-1a over a byte buffer (grid fingerprints in tests and golden files). */
 uint32_t orc_fnv1a32(const uint8_t* p, size_t n) {
   uint32_t h = 0x811c9dc5u;

@@ -18,6 +18,11 @@ def test_clamp_add_monoid(oracle):
     assert oracle.L.orc_clamp_monoid_check(20000, 12345) == 0
 
 
+def test_time_slice_map_representation(oracle):
+    """(f(lo_min), f(lo_max), saturating sum) reproduces any slice's effect on any start value, and composes."""
+    assert oracle.L.orc_slice_map_check(3000, 7) == 0
+
+
 def test_saturating_updates_do_not_commute():
     """78 +6 -1 = 79 but 78 -1 +6 = 80 -- why the kernels never reorder a cell's updates."""
     c = lambda v: max(-80, min(80, v))

@@ -263,6 +263,31 @@ def test_result_is_independent_of_subtile_size(gpu, oracle, synth):
         gpu.set_engine(0, 0)
 
 
+def test_time_slices_compose_exactly(gpu, oracle, synth):
+    """A log cut into S concurrent time slices (slice 0 on values, later slices as clamp-add maps, composed
+    per cell afterwards) must give the same bytes as the sequential replay, for any S and any tile size."""
+    w = synth.scaled(synth.CONFIGS["c2"], n_samples=9000)
+    d = synth.generate(w)
+    p = w.params()
+    want, U = oracle_grids(oracle, p, d)
+    w1 = synth.scaled(synth.CONFIGS["c3"], n_flights=3, n_samples=1300)
+    d1 = synth.generate(w1)
+    p1 = w1.params()
+    want1, _ = oracle_grids(oracle, p1, d1)
+    gpu.set_engine(1, 0)
+    try:
+        for (sw, sh, S) in [(0, 0, 2), (0, 0, 5), (64, 24, 9), (0, 0, 64), (80, 80, 3)]:
+            gpu.set_tuning(sw, sh, S)
+            got, st = gpu.replay(p, d["x_true"], d["y_true"], d["frame_yaw_deg"], d["ranges"])
+            assert np.array_equal(got, want), ((sw, sh, S), first_diff(got, want))
+            assert st["ray_cell_updates"] == U
+            got1, _ = gpu.replay(p1, d1["x_true"], d1["y_true"], d1["frame_yaw_deg"], d1["ranges"])
+            assert np.array_equal(got1, want1), ((sw, sh, S), first_diff(got1, want1))
+    finally:
+        gpu.set_tuning(0, 0, 0)
+        gpu.set_engine(0, 0)
+
+
 def test_chained_replays_and_row_bands_via_device_api(gpu, oracle, synth):
     """accumulate: first half then second half == whole log; row bands owned by different 'GPUs'
     union to the whole grid (the config-4 partitioning), all through uqs_replay_dev on device pointers."""
