@@ -188,6 +188,35 @@ int uqs_beam_cells(const uqs_params* p, int n_frames,
  * (parity test hook for SURVEY.md Appendix B). */
 int uqs_sincosf_batch(size_t n, const float* ang, float* sin_out, float* cos_out);
 
+/* ---- rows either side of the path ------------------------------- */
+
+/* N1: raw ToF scans -> tof_beams_m.  raw = [n][512] bytes, 4 sensors (F,R,B,L) x 64 cells x u16 LE mm
+ * (scanrec_t.grid_raw, uav_local_nav.c:1546; wire format tof_esp32.ino:192-211).  Per column the
+ * second-smallest valid row (robust_col_dist_m, :1320-1342).  dir_min (may be NULL) = tof_min_m[4]. */
+int uqs_beams_from_scans(long long n_frames, const uint8_t* raw, float max_range_m, float* beams_out /* [n][32] */,
+                         float* dir_min_out /* [n][4] or NULL */);
+int uqs_beams_from_scans_dev(long long n_frames, const uint8_t* raw_dev, float max_range_m, float* beams_dev,
+                             float* dir_min_dev);
+
+/* N2: replay ONE log exactly as log_tick() does with recentering enabled (uav_local_nav.c:1629-1635:
+ * map_recentre_if_needed(pose) before every update).  origin_out = final map origin; events_out receives
+ * up to max_events {frame, sx_cells, sy_cells} triples. */
+int uqs_replay_recentering(const uqs_params* p, int n_frames, const float* x, const float* y, const float* yaw_deg,
+                           const float* ranges, int8_t* grid_out, float origin_out[2], int* n_events_out,
+                           int* events_out, int max_events, uqs_stats* stats);
+
+/* N3: frontier_score_dir() (uav_local_nav.c:356-385) for n queries against one host grid. */
+int uqs_frontier_scores(const uqs_params* p, const int8_t* grid, int n, const float* x, const float* y,
+                        const float* yaw_deg, const float* offset_deg, int* scores_out);
+
+/* N4: reader of scanlog.bin ("SCLOG2\n" + packed 569-byte scanrec_t records, uav_local_nav.c:1505,1522-1547).
+ * Returns the number of qualifying records (> max_records means the buffers were too small), < 0 on error.
+ * Records whose pose is NaN (:1559-1561) are skipped unless keep_nan_pose != 0.  Any output may be NULL. */
+long uqs_scanlog_read(const char* path, int keep_nan_pose, long max_records, uint32_t* host_ms, uint32_t* scan_ms,
+                      float* x_m, float* y_m, float* yaw_deg, float* alt_m, float* of_rate_x, float* of_rate_y,
+                      uint8_t* of_q, uint8_t* kf_flags, uint8_t* grid_raw);
+long uqs_scanlog_count(const char* path, int keep_nan_pose);
+
 /* Measured on-chip read-modify-write ceiling: every warp of a full grid does
  * conflict-free byte RMWs on its shared-memory sub-tile.  Returns updates/s. */
 int uqs_measure_rmw_peak(double* updates_per_s);
@@ -219,6 +248,9 @@ extern uint8_t  pending_kf_flags;    /* |= KF_MAP_RECENTER (1u<<5) on recenter  
 bool world_to_grid(float x, float y, int* gx, int* gy);                          /* :205 */
 void raycast_update(float x0, float y0, float x1, float y1, bool hit_occ);       /* :241 */
 void map_update_from_beams(float x_m, float y_m, float yaw_deg);                 /* :280 */
+void map_recenter_shift(int sx_cells, int sy_cells);                             /* :308 */
+void map_recentre_if_needed(float x_m, float y_m);                               /* :324 */
+int  frontier_score_dir(float x_m, float y_m, float yaw_deg, float offset_deg);  /* :356 */
 
 #ifdef __cplusplus
 }

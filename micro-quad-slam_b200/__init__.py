@@ -83,6 +83,8 @@ _EXPORTS = [
     "uqs_set_profiling", "uqs_profile_collect", "uqs_set_host_chunk",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
     "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
+    "uqs_beams_from_scans", "uqs_beams_from_scans_dev", "uqs_replay_recentering", "uqs_frontier_scores",
+    "uqs_scanlog_read", "uqs_scanlog_count", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
     # drop-in symbols
     "uqs_dropin_configure", "uqs_dropin_flush", "uqs_dropin_upload", "map_reset",
     "occ_grid", "map_inited", "map_origin_x", "map_origin_y", "tof_beams_m", "pending_kf_flags",
@@ -120,6 +122,18 @@ def lib() -> C.CDLL:
     L.uqs_beam_cells.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp]
     L.uqs_sincosf_batch.argtypes = [C.c_size_t, vp, vp, vp]
     L.uqs_measure_rmw_peak.argtypes = [C.POINTER(C.c_double)]
+    L.uqs_beams_from_scans.argtypes = [C.c_longlong, vp, C.c_float, vp, vp]
+    L.uqs_replay_recentering.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, ip, C.POINTER(Stats)]
+    L.uqs_frontier_scores.argtypes = [C.POINTER(Params), vp, ip, vp, vp, vp, vp, vp]
+    L.uqs_scanlog_read.restype = C.c_long
+    L.uqs_scanlog_read.argtypes = [C.c_char_p, ip, C.c_long] + [vp] * 11
+    L.uqs_scanlog_count.restype = C.c_long
+    L.uqs_scanlog_count.argtypes = [C.c_char_p, ip]
+    L.map_recenter_shift.argtypes = [ip, ip]
+    L.map_recenter_shift.restype = None
+    L.map_recentre_if_needed.argtypes = [C.c_float, C.c_float]
+    L.map_recentre_if_needed.restype = None
+    L.frontier_score_dir.argtypes = [C.c_float] * 4
     L.uqs_dropin_configure.argtypes = [C.POINTER(Params)]
     L.world_to_grid.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.world_to_grid.restype = C.c_bool
@@ -284,6 +298,56 @@ def sincosf_batch(ang):
     return s, c
 
 
+def beams_from_scans(raw, max_range_m: float = 4.0):
+    """N1: raw [n,512] u8 (u16 LE mm, F/R/B/L x 8x8) -> (beams [n,32], dir_min [n,4])."""
+    raw = np.ascontiguousarray(raw, np.uint8).reshape(-1, 512)
+    n = raw.shape[0]
+    beams, dmin = np.empty((n, 32), np.float32), np.empty((n, 4), np.float32)
+    _check(lib().uqs_beams_from_scans(n, _ptr(raw), max_range_m, _ptr(beams), _ptr(dmin)))
+    return beams, dmin
+
+
+def replay_recentering(p: Params, x, y, yaw_deg, ranges):
+    """N2: one log with the reference's recentering honoured -> (grid, origin, events [[frame,sx,sy]...], stats)."""
+    x, y, yaw_deg = _f32(x).ravel(), _f32(y).ravel(), _f32(yaw_deg).ravel()
+    n = x.size
+    ranges = _f32(ranges).reshape(n, BEAMS_PER_FRAME)
+    grid = np.empty((p.H, p.W), np.int8)
+    origin = np.zeros(2, np.float32)
+    n_ev = C.c_int(0)
+    ev = np.zeros((256, 3), np.int32)
+    st = Stats()
+    _check(lib().uqs_replay_recentering(C.byref(p), n, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(grid), _ptr(origin),
+                                        C.byref(n_ev), _ptr(ev), 256, C.byref(st)))
+    return grid, (float(origin[0]), float(origin[1])), ev[:min(n_ev.value, 256)].copy(), st.as_dict()
+
+
+def frontier_scores(p: Params, grid, x, y, yaw_deg, offset_deg):
+    """N3: frontier_score_dir for n queries against one grid."""
+    g = np.ascontiguousarray(grid, np.int8).reshape(p.H, p.W)
+    x, y, yaw_deg, offset_deg = (_f32(a).ravel() for a in (x, y, yaw_deg, offset_deg))
+    out = np.empty(x.size, np.int32)
+    _check(lib().uqs_frontier_scores(C.byref(p), _ptr(g), x.size, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(offset_deg), _ptr(out)))
+    return out
+
+
+def scanlog_read(path: str, keep_nan_pose: bool = False) -> dict:
+    """N4: scanlog.bin -> SoA numpy arrays (host file I/O in the C library)."""
+    L = lib()
+    n = L.uqs_scanlog_count(path.encode(), int(keep_nan_pose))
+    if n < 0:
+        raise UqsError(ERR_BAD_ARG, f"cannot read scan log {path} (code {n})")
+    d = {"host_ms": np.empty(n, np.uint32), "scan_ms": np.empty(n, np.uint32), "x_m": np.empty(n, np.float32),
+         "y_m": np.empty(n, np.float32), "yaw_deg": np.empty(n, np.float32), "alt_m": np.empty(n, np.float32),
+         "of_rate_x": np.empty(n, np.float32), "of_rate_y": np.empty(n, np.float32), "of_q": np.empty(n, np.uint8),
+         "kf_flags": np.empty(n, np.uint8), "grid_raw": np.empty((n, 512), np.uint8)}
+    got = L.uqs_scanlog_read(path.encode(), int(keep_nan_pose), n, *(_ptr(d[k]) for k in
+                             ("host_ms", "scan_ms", "x_m", "y_m", "yaw_deg", "alt_m", "of_rate_x", "of_rate_y", "of_q", "kf_flags", "grid_raw")))
+    if got != n:
+        raise UqsError(ERR_BAD_ARG, f"scan log changed while reading ({got} != {n})")
+    return d
+
+
 def measure_rmw_peak() -> float:
     v = C.c_double(0)
     _check(lib().uqs_measure_rmw_peak(C.byref(v)))
@@ -326,6 +390,18 @@ class DropIn:
         gx, gy = C.c_int(-1), C.c_int(-1)
         ok = self.L.world_to_grid(np.float32(x), np.float32(y), C.byref(gx), C.byref(gy))
         return bool(ok), gx.value, gy.value
+
+    def map_recentre_if_needed(self, x, y):
+        self.L.map_recentre_if_needed(np.float32(x), np.float32(y))
+
+    def frontier_score_dir(self, x, y, yaw, off) -> int:
+        return int(self.L.frontier_score_dir(np.float32(x), np.float32(y), np.float32(yaw), np.float32(off)))
+
+    def origin(self):
+        return self._g(C.c_float, "map_origin_x").value, self._g(C.c_float, "map_origin_y").value
+
+    def kf_flags(self) -> int:
+        return self._g(C.c_uint8, "pending_kf_flags").value
 
     def grid(self) -> np.ndarray:
         self.L.uqs_dropin_flush()

@@ -124,7 +124,7 @@ int uqs_dropin_configure(const uqs_params* p) {
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&D.qthird, kQueueCap * 4, cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&D.qranges, kQueueCap * 128, cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&D.qkind, kQueueCap, cudaHostAllocDefault);
-  if (e == cudaSuccess) e = cudaHostAlloc((void**)&D.w2g, 16, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&D.w2g, 32, cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaMemsetAsync(D.d_grid, 0, cells, g_ctx.stream());
   if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream());
   if (e != cudaSuccess) {
@@ -209,6 +209,75 @@ void raycast_update(float x0, float y0, float x1, float y1, bool hit_occ) {
 void map_update_from_beams(float x_m, float y_m, float yaw_deg) {
   if (!map_inited) return;      /* :281 */
   enqueue(0, x_m, y_m, yaw_deg, &tof_beams_m[0][0]);
+}
+
+/* ---- N2 / N3 drop-ins (uav_local_nav.c:308-385) ------------------------------------------------ */
+
+void map_recenter_shift(int sx_cells, int sy_cells) {
+  if (!D.configured) die("map_recenter_shift() before uqs_dropin_configure()");
+  if (flush_queue()) die("replay failed");
+  const size_t cells = (size_t)D.cfg.W * D.cfg.H;
+  int rc = g_ctx.out_grids.ensure(cells);
+  if (rc) die("allocation failed");
+  cudaStream_t st = g_ctx.stream();
+  k_recenter_shift<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(D.d_grid, (int8_t*)g_ctx.out_grids.p, D.cfg.W, D.cfg.H,
+                                                                    sx_cells, sy_cells);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(D.d_grid, g_ctx.out_grids.p, cells, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cuda_fail(e, "map_recenter_shift"); die("recenter shift failed"); }
+  g_ctx.launches += 1;
+  D.mirror_stale = true;
+}
+
+void map_recentre_if_needed(float x_m, float y_m) {
+  if (!map_inited) return;                                     /* :325 */
+  if (!D.configured) die("map_recentre_if_needed() before uqs_dropin_configure()");
+  int* dptr = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer((void**)&dptr, D.w2g, 0);
+  if (e == cudaSuccess) {
+    k_recenter_decide_one<<<1, 1, 0, g_ctx.stream()>>>(D.cfg.res_m, D.cfg.size_m, map_origin_x, map_origin_y, x_m, y_m, dptr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream());
+  if (e != cudaSuccess) { cuda_fail(e, "map_recentre_if_needed"); die("recenter decision failed"); }
+  g_ctx.launches += 1;
+  if (!D.w2g[0]) return;
+  const int sx = D.w2g[1], sy = D.w2g[2];
+  map_recenter_shift(sx, sy);                                  /* flushes updates queued under the old origin */
+  memcpy(&map_origin_x, &D.w2g[3], 4);
+  memcpy(&map_origin_y, &D.w2g[4], 4);
+  pending_kf_flags |= (1u << 5);                               /* KF_MAP_RECENTER, :225,:350 */
+  printf("Map recenter: shift (%d,%d) cells => new origin (%.2f,%.2f)\n", sx, sy, map_origin_x, map_origin_y);
+}
+
+int frontier_score_dir(float x_m, float y_m, float yaw_deg, float offset_deg) {
+  if (!map_inited) return 0;                                   /* :357 */
+  if (!D.configured) die("frontier_score_dir() before uqs_dropin_configure()");
+  if (flush_queue()) die("replay failed");                     /* reads must see every queued update */
+  uqs_params p = D.cfg;
+  p.origin_x = map_origin_x;
+  p.origin_y = map_origin_y;
+  DevParams dp;
+  if (make_dev_params(&p, &dp)) die("bad map parameters");
+  int rc = g_ctx.in_x.ensure(64);
+  if (!rc) rc = g_ctx.w->counters.ensure(64 * 8);
+  if (rc) die("allocation failed");
+  cudaStream_t st = g_ctx.stream();
+  const float q[4] = { x_m, y_m, yaw_deg, offset_deg };
+  float* dq = (float*)g_ctx.in_x.p;
+  int* dptr = nullptr;
+  cudaError_t e = cudaMemcpyAsync(dq, q, 16, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&dptr, D.w2g, 0);
+  if (e == cudaSuccess) {
+    k_frontier_scores<<<1, 32, 0, st>>>(dp, D.d_grid, 1, dq, dq + 1, dq + 2, dq + 3, dptr,
+                                         (unsigned long long*)g_ctx.w->counters.p + 24);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cuda_fail(e, "frontier_score_dir"); die("frontier kernel failed"); }
+  g_ctx.launches += 1;
+  return D.w2g[0];
 }
 
 }  // extern "C"

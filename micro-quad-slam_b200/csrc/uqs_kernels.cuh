@@ -71,5 +71,11 @@ __global__ void k_compose_slices(int8_t* grids, const uint32_t* maps, int n_flig
 cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm);
 cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);
+// uqs_next.cu
+__global__ void k_recenter_decide_one(float res, float size_m, float ox, float oy, float x, float y, int* out);
+__global__ void k_recenter_shift(const int8_t* src, int8_t* dst, int W, int H, int sx, int sy);
+__global__ void k_frontier_scores(DevParams p, const int8_t* grid, int n, const float* x, const float* y,
+                                  const float* yaw_deg, const float* offset_deg, int* scores,
+                                  unsigned long long* domain_errors);
 
 }  // namespace uqs

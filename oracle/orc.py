@@ -56,6 +56,10 @@ class Oracle:
         L.orc_magic_division_check.restype = C.c_long
         L.orc_clamp_monoid_check.restype = C.c_long
         L.orc_clamp_monoid_check.argtypes = [C.c_long, C.c_uint64]
+        L.orc_beams_from_scan.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_beams_from_scan.restype = None
+        L.orc_replay_recentering.argtypes = [C.c_void_p, C.c_void_p, C.c_long] + [C.c_void_p] * 4 + [C.POINTER(C.c_long)]
+        L.orc_frontier_score_dir.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 4
         L.orc_slice_map_check.restype = C.c_long
         L.orc_slice_map_check.argtypes = [C.c_long, C.c_uint64]
         L.orc_fnv1a32.restype = C.c_uint32
@@ -98,6 +102,30 @@ class Oracle:
         for i in range(n):
             self.L.orc_beam_cells(C.byref(p), x[i], y[i], yaw_deg[i], _vp(ranges[i]), _vp(cells[i]), _vp(origin[i]))
         return cells, origin
+
+    # --- next rows N1-N3 ---------------------------------------------------------------------
+    def beams_from_scans(self, raw, max_range=4.0):
+        raw = np.ascontiguousarray(raw, np.uint8).reshape(-1, 512)
+        n = raw.shape[0]
+        beams, dmin = np.empty((n, 32), np.float32), np.empty((n, 4), np.float32)
+        for i in range(n):
+            self.L.orc_beams_from_scan(_vp(raw[i]), max_range, _vp(beams[i]), _vp(dmin[i]))
+        return beams, dmin
+
+    def replay_recentering(self, p, x, y, yaw_deg, ranges):
+        """log_tick() with recentering: returns (grid, origin (x,y), n_events, updates); p is not modified."""
+        q = type(p)()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+        x, y, yaw_deg = (np.ascontiguousarray(a, np.float32).ravel() for a in (x, y, yaw_deg))
+        ranges = np.ascontiguousarray(ranges, np.float32).reshape(x.size, 32)
+        grid = np.zeros((p.H, p.W), np.int8)
+        U = C.c_long(0)
+        n_ev = self.L.orc_replay_recentering(C.byref(q), _vp(grid), x.size, _vp(x), _vp(y), _vp(yaw_deg), _vp(ranges), C.byref(U))
+        return grid, (float(q.origin_x), float(q.origin_y)), int(n_ev), int(U.value)
+
+    def frontier_score(self, p, grid, x, y, yaw_deg, offset_deg) -> int:
+        g = np.ascontiguousarray(grid, np.int8)
+        return int(self.L.orc_frontier_score_dir(C.byref(p), _vp(g), x, y, yaw_deg, offset_deg))
 
     # --- P0 (builder-defined) --------------------------------------------------------------
     def pose_integrate(self, t_ms, rx, ry, h, yaw_deg, q):
@@ -190,3 +218,21 @@ class Reference:
 
     def recentered(self) -> bool:
         return bool(self.L.ref_recentered())
+
+    def origin(self):
+        return float(self.L.ref_origin_x()), float(self.L.ref_origin_y())
+
+    def frontier_score(self, x, y, yaw_deg, offset_deg) -> int:
+        return int(self.L.ref_frontier_score_dir(np.float32(x), np.float32(y), np.float32(yaw_deg), np.float32(offset_deg)))
+
+    def set_grid(self, grid):
+        np.ctypeslib.as_array(self.L.ref_grid(), shape=(self.H, self.W))[:] = grid
+
+    def beams_from_frame(self, raw512) -> np.ndarray:
+        """compute_beams_and_minima on a 518-byte wire frame built around the 512 raw bytes."""
+        frame = np.zeros(518, np.uint8)
+        frame[0] = 0xA5
+        frame[5:517] = np.ascontiguousarray(raw512, np.uint8).ravel()
+        out = np.empty(32, np.float32)
+        self.L.ref_beams_from_frame(_vp(frame), _vp(out))
+        return out

@@ -150,6 +150,109 @@ void orc_beam_cells(const uqs_params* p, float px, float py, float yaw_deg, cons
 }
 
 /* ------------------------------------------------------------------ */
+/* rows either side of the path               */
+/* ------------------------------------------------------------------ */
+
+/* N1: robust_col_dist_m() + compute_beams_and_minima(), uav_local_nav.c:1320-1359.
+ * raw = 512 bytes: 4 sensors x 64 cells x u16 LE mm (the frame payload at &frame[5], :1345). */
+void orc_beams_from_scan(const uint8_t* raw, float max_range, float* beams /* [32] */, float* dir_min /* [4] or NULL */) {
+  for (int d = 0; d < 4; d++) {
+    const uint8_t* sensor = raw + d * 128;
+    float lowest_dir = NAN;
+    for (int c = 0; c < 8; c++) {
+      float first = NAN, runner_up = NAN;
+      for (int row = 0; row < 8; row++) {
+        const uint8_t* q = sensor + (row * 8 + c) * 2;
+        const unsigned mm = (unsigned)q[0] | ((unsigned)q[1] << 8);
+        if (mm == 0xFFFFu || mm == 0u) continue;
+        float metres = (float)mm * 0.001f;
+        if (metres <= 0.02f) continue;
+        if (metres > max_range) metres = max_range;
+        if (isnan(first) || metres < first) { runner_up = first; first = metres; }
+        else if (isnan(runner_up) || metres < runner_up) runner_up = metres;
+      }
+      const float chosen = !isnan(runner_up) ? runner_up : first;
+      beams[d * 8 + c] = chosen;
+      if (!isnan(chosen) && (isnan(lowest_dir) || chosen < lowest_dir)) lowest_dir = chosen;
+    }
+    if (dir_min) dir_min[d] = lowest_dir;
+  }
+}
+
+/* N2: map_recenter_shift(), uav_local_nav.c:308-322 */
+void orc_recenter_shift(const uqs_params* p, int8_t* grid, int sx, int sy) {
+  const size_t cells = (size_t)p->W * p->H;
+  int8_t* tmp = (int8_t*)calloc(cells, 1);
+  for (int yy = 0; yy < p->H; yy++) {
+    const int v = yy + sy;
+    if (v < 0 || v >= p->H) continue;
+    for (int xx = 0; xx < p->W; xx++) {
+      const int u = xx + sx;
+      if (u < 0 || u >= p->W) continue;
+      tmp[(size_t)yy * p->W + xx] = grid[(size_t)v * p->W + u];
+    }
+  }
+  memcpy(grid, tmp, cells);
+  free(tmp);
+}
+
+/* N2: map_recentre_if_needed(), uav_local_nav.c:324-353; moves p->origin and shifts the grid; returns 1 if it did */
+int orc_recentre_if_needed(uqs_params* p, int8_t* grid, float px, float py, int* sx_out, int* sy_out) {
+  const float half = p->size_m * 0.5f;
+  const float thresh = half * 0.60f;
+  const float ddx = px - p->origin_x, ddy = py - p->origin_y;
+  if (fabsf(ddx) < thresh && fabsf(ddy) < thresh) return 0;
+  int sx = (int)lrintf(ddx / p->res_m), sy = (int)lrintf(ddy / p->res_m);
+  const int cap = (int)(half / p->res_m * 0.5f);
+  if (sx > cap) sx = cap;
+  if (sx < -cap) sx = -cap;
+  if (sy > cap) sy = cap;
+  if (sy < -cap) sy = -cap;
+  if (sx == 0 && sy == 0) return 0;
+  orc_recenter_shift(p, grid, sx, sy);
+  p->origin_x += (float)sx * p->res_m;
+  p->origin_y += (float)sy * p->res_m;
+  if (sx_out) *sx_out = sx;
+  if (sy_out) *sy_out = sy;
+  return 1;
+}
+
+/* log_tick() with recentering, uav_local_nav.c:1629-1635; returns the number of recenter events */
+int orc_replay_recentering(uqs_params* p, int8_t* grid, long n_frames, const float* x, const float* y,
+                           const float* yaw_deg, const float* ranges, long* updates) {
+  int events = 0;
+  long visited = 0;
+  for (long i = 0; i < n_frames; i++) {
+    events += orc_recentre_if_needed(p, grid, x[i], y[i], NULL, NULL);
+    visited += orc_frame(p, grid, x[i], y[i], yaw_deg[i], ranges + i * UQS_BEAMS_PER_FRAME);
+  }
+  if (updates) *updates = visited;
+  return events;
+}
+
+/* N3: frontier_score_dir(), uav_local_nav.c:356-385 */
+int orc_frontier_score_dir(const uqs_params* p, const int8_t* grid, float px, float py, float yaw_deg, float offset_deg) {
+  static const float fan_deg[3] = { 0.0f, 15.0f, -15.0f };
+  const float reach = 2.5f;
+  const float stride = p->res_m * 2.0f;
+  int n_unknown = 0, n_free = 0, n_occ = 0;
+  for (int r = 0; r < 3; r++) {
+    const float a = (yaw_deg + offset_deg + fan_deg[r]) * ((float)M_PI / 180.0f);
+    float sn, cs;
+    sincosf(a, &sn, &cs);
+    for (float t = stride; t <= reach; t += stride) {
+      int gx, gy;
+      if (!orc_world_to_grid(p, px + t * cs, py + t * sn, &gx, &gy)) break;
+      const int8_t v = grid[(size_t)gy * p->W + gx];
+      if (v >= -1 && v <= 1) n_unknown++;
+      else if (v > 10) n_occ++;
+      else if (v < -10) n_free++;
+    }
+  }
+  return n_unknown * 3 + n_free - n_occ * 4;
+}
+
+/* ------------------------------------------------------------------ */
 /* P0 -- builder-defined dead reckoning  */
 /* ------------------------------------------------------------------ */
 void orc_pose_integrate(long n, const uint32_t* t_ms, const float* rate_x, const float* rate_y,
