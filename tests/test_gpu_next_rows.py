@@ -97,3 +97,34 @@ def test_scanlog_to_grid_end_to_end(gpu, oracle, synth, tmp_path):
     want, U = oracle.replay(p, log["x_m"], log["y_m"], log["yaw_deg"], ob)
     assert np.array_equal(grid[0], want), first_diff(grid[0], want)
     assert st["ray_cell_updates"] == U > 100000
+
+
+def test_plain_c_harness_links_and_matches(gpu, oracle, synth, tmp_path):
+    """examples/replay_scanlog.c: host code in plain C against include/uqs_mapping.h; batch route and drop-in
+    route must agree with each other and with the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "replay_scanlog")
+    lib_dir = os.path.join(root, "micro-quad-slam_b200")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "replay_scanlog.c"),
+                        "-L", lib_dir, "-luqs_mapping", "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    w = synth.scaled(synth.CONFIGS["c1"], n_samples=300)
+    d = synth.generate(w)
+    recs = []
+    for i in range(300):
+        mm = np.repeat(np.clip(np.nan_to_num(d["ranges"][0, i], nan=65.535) * 1000.0, 0, 65535), 8).reshape(4, 8, 8).transpose(0, 2, 1)
+        recs.append({"host_ms": 20 * i, "scan_ms": 20 * i, "x": float(d["x_true"][0, i]), "y": float(d["y_true"][0, i]),
+                     "yaw": float(d["yaw_deg"][0, i]), "alt": 0.5, "rf": 0.5, "ofx": 0.0, "ofy": 0.0, "q": 200, "kf": 0,
+                     "raw": mm.astype("<u2").reshape(-1).view(np.uint8)})
+    path = str(tmp_path / "scanlog.bin")
+    write_scanlog(path, recs)
+    out = subprocess.run([exe, path, "400", "0.05"], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=lib_dir))
+    assert out.returncode == 0 and "MATCH" in out.stdout, out.stdout + out.stderr
+    log = gpu.scanlog_read(path)
+    p = w.params()
+    p.origin_x, p.origin_y = log["x_m"][0], log["y_m"][0]
+    ob, _ = oracle.beams_from_scans(log["grid_raw"])
+    want, U = oracle.replay(p, log["x_m"], log["y_m"], log["yaw_deg"], ob)
+    assert f"fnv_batch={oracle.fnv1a32(want):08x}" in out.stdout and f"updates={U}" in out.stdout, out.stdout
