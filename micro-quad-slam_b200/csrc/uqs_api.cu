@@ -101,7 +101,7 @@ int make_dev_params(const uqs_params* p, DevParams* d) {
 
 // sub-tile geometry for a grid of W columns and `rows` owned rows, aiming at `target`-cell sub-tiles
 static void choose_tiles(int W, int rows, int target, int* sw, int* sh, int* nsx, int* nsy) {
-  auto pick = [target](int extent, int forced, int* size, int* count) {
+  auto pick = [](int extent, int forced, int target, int* size, int* count) {
     if (forced > 0) {
       *size = std::min(forced, extent);
     } else {
@@ -112,8 +112,10 @@ static void choose_tiles(int W, int rows, int target, int* sw, int* sh, int* nsx
     }
     *count = (extent + *size - 1) / *size;
   };
-  pick(W, g_ctx.tune_sw, sw, nsx);
-  pick(rows, g_ctx.tune_sh, sh, nsy);
+  // measured on the 400x400 ensemble: 80 wide x 100 high beats 80x80 by ~4 % (fewer row crossings per ray
+  // for the same number of resident warps); small (time-sliced) tiles stay square
+  pick(W, g_ctx.tune_sw, target, sw, nsx);
+  pick(rows, g_ctx.tune_sh, target >= 80 ? target + target / 4 : target, sh, nsy);
 }
 
 int replay_device(const DevParams& dp, int n_flights, int n_frames, const float* x, const float* y,

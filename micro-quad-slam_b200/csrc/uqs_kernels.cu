@@ -186,7 +186,7 @@ size_t pose_scan_state_bytes() { return sizeof(ScanState); }
 // kind == nullptr: every entry is a frame (pose + 32 ranges).
 // kind[i] == 1   : entry i is one raw ray raycast_update(x0,y0,x1,y1,hit) stored as
 //                  x=x0, y=y0, yaw=x1, ranges[0]=y1, ranges[1]=hit (drop-in symbol only).
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 2)
 k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __restrict__ x,
             const float* __restrict__ y, const float* __restrict__ yaw_deg,
             const float* __restrict__ ranges, const uint8_t* __restrict__ kind, int want_k0,
