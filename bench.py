@@ -247,6 +247,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("UQS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     m.init(local)                                   # fails loudly if the CUDA library cannot run
     m.set_stream(torch.cuda.current_stream().cuda_stream)
