@@ -157,6 +157,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank (and its pinned allocations, by first touch) on the CPUs local to its GPU; on multi-socket
+    boxes this keeps H2D/D2H traffic of the e2e path off the inter-socket link.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -246,6 +265,7 @@ def main():
                          f"--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    local_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("UQS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -381,7 +401,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8",
            "data": "synthetic", "config": describe(w, world), "frames_per_s": F * NF * world / (ms_per_step * 1e-3),
            "ray_cell_updates_per_step": total_updates, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-           "gpu_launches": int(launches), "clocks": clk}
+           "gpu_launches": int(launches), "clocks": clk, "host": {"cpus": os.cpu_count(), "rank_local_cpus": local_cpus}}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -158,23 +158,16 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   const int tile_bytes = slices > 1 ? std::max(pitch * sh, pitch_cells * sh * 4) : pitch * sh;
   size_t smem = (size_t)tile_bytes * kReplayWarps;
 
-  // engine: whole grid resident in one CTA's shared memory (frame-synchronous) when it fits
-  // and the launch owns the whole grid; otherwise warp-owned sub-tiles
-  int fpitch = (dp.W + 3) & ~3;
-  if (((fpitch >> 2) & 1) == 0 && (size_t)(fpitch + 4) * dp.H <= kFlightSmemMax) fpitch += 4;
-  const int nw = g_ctx.flight_warps == 8 ? 8 : (g_ctx.flight_warps == 32 ? 32 : 16);
-  int ring_size = 256;                                    // per-warp collision table (power of two)
-  while (ring_size > 32 && (size_t)fpitch * dp.H + (size_t)ring_size * nw > kFlightSmemMax) ring_size >>= 1;
-  const size_t fsmem = (size_t)fpitch * dp.H + (size_t)ring_size * nw;
-  // auto: the frame-synchronous resident engine wins only in a narrow window of ~0.75..2 flights per SM
-  // (measured): below it the time-sliced sub-tile engine fills the chip better, above it plain sub-tiles do
-  const bool fits = row0 == 0 && rows == dp.H && fsmem <= kFlightSmemMax;
-  const bool resident = fits && (g_ctx.engine == 2 || (g_ctx.engine == 0 && 4 * n_flights >= 3 * g_ctx.sm_count && n_flights <= 2 * g_ctx.sm_count));
-  if (g_ctx.engine == 2 && !fits) {
-    set_error("engine 2 (grid resident per CTA) needs the whole %dx%d grid in %zu B of shared memory", dp.W, dp.H, kFlightSmemMax);
+  // Engine 2 keeps, per CTA, the bounding box of the cells one flight can touch resident in shared memory
+  // (frame-synchronous).  Whether it fits -- and how many CTAs share an SM -- is only known
+  // after the ray set-up of a chunk (k_flight_boxes), so the choice is made per chunk below.
+  // warps per resident CTA: 8 when there are flights for every CTA slot, 16 when flights are scarce
+  const int nw = g_ctx.flight_warps ? g_ctx.flight_warps : (n_flights >= 4 * g_ctx.sm_count ? 8 : 16);
+  const bool may_reside = g_ctx.engine != 1 && row0 == 0 && rows == dp.H;
+  if (g_ctx.engine == 2 && !may_reside) {
+    set_error("engine 2 (resident) cannot replay a row band");
     return UQS_ERR_BAD_ARG;
   }
-  if (resident) smem = fsmem;
   if (smem > 227u * 1024u) {
     set_error("sub-tile %dx%d needs %zu B of shared memory per CTA (> 227 KB)", sw, sh, smem);
     return UQS_ERR_BAD_ARG;
@@ -197,15 +190,10 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   }
 
   int ctas_per_sm = 0;
-  if (resident) {
-    e = flights_prepare(nw, smem, &ctas_per_sm);
-    if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights attributes");
-  } else {
-    e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_replay_tiles, kReplayThreads, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "occupancy(k_replay_tiles)");
-  }
+  e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_replay_tiles, kReplayThreads, smem);
+  if (e != cudaSuccess) return cuda_fail(e, "occupancy(k_replay_tiles)");
   if (ctas_per_sm < 1) { set_error("replay kernel does not fit on an SM (smem %zu)", smem); return UQS_ERR_CUDA; }
 
   for (int f0 = 0; f0 < n_flights; f0 += chunk) {
@@ -213,32 +201,67 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     const size_t fo = (size_t)f0 * n_frames;
     KernelTimer t_setup(1);
     k_ray_setup<<<(unsigned)(nf * gpf), 1024, 0, st>>>(
-        dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, resident ? 1 : 0,
+        dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, may_reside ? 1 : 0,
         (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
     e = cudaGetLastError();
     t_setup.stop();
     if (e != cudaSuccess) return cuda_fail(e, "k_ray_setup launch");
 
-    if (resident) {
-      FlightArgs FA;
-      FA.frames = (const uint4*)g_ctx.w->frames.p;
-      FA.rays = (const uint2*)g_ctx.w->rays.p;
-      FA.grids = grids + (size_t)f0 * dp.W * dp.H;
-      FA.job_counter = counters + 8;
-      FA.n_flights = nf; FA.n_frames = n_frames;
-      FA.W = dp.W; FA.H = dp.H; FA.pitch = fpitch; FA.ring_size = ring_size;
-      FA.lo_free = dp.lo_free; FA.lo_occ = dp.lo_occ; FA.lo_min = dp.lo_min; FA.lo_max = dp.lo_max;
-      FA.end_nohit = dp.end_nohit;
-      FA.accumulate = accumulate;
-      e = cudaMemsetAsync(FA.job_counter, 0, sizeof(unsigned long long), st);
-      if (e != cudaSuccess) return cuda_fail(e, "memset job counter");
-      const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)ctas_per_sm * g_ctx.sm_count);
-      KernelTimer t_rep(2);
-      e = flights_launch(nw, fgrid, smem, st, FA);
-      t_rep.stop();
-      if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights launch");
-      g_ctx.launches += 2;
-      continue;
+    if (may_reside) {
+      // touched bounding box per flight -> shared memory per CTA -> CTAs per SM -> engine choice
+      if ((rc = g_ctx.w->boxes.ensure((size_t)nf * sizeof(int4)))) return rc;
+      int* d_dims = (int*)(counters + 32);
+      e = cudaMemsetAsync(d_dims, 0, 2 * sizeof(int), st);
+      if (e == cudaSuccess)
+        e = flight_boxes_launch(nf, gpf, (const uint2*)g_ctx.w->groups.p, dp.W, dp.H, (int4*)g_ctx.w->boxes.p, d_dims, st);
+      int dims[2] = { 0, 0 };
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dims, d_dims, sizeof(dims), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "k_flight_boxes");
+      g_ctx.launches += 1;
+      const int bw = std::max(dims[0], 4), bh = std::max(dims[1], 1);
+      int fpitch = (bw + 3) & ~3;
+      if (((fpitch >> 2) & 1) == 0) fpitch += 4;
+      int ring_size = 256;                                  // per-warp collision table (power of two)
+      const size_t region = (size_t)fpitch * bh;
+      while (ring_size > 32 && region + (size_t)(ring_size + 4) * nw > kFlightSmemMax) ring_size >>= 1;
+      const size_t fsmem = region + (size_t)(ring_size + 4) * nw;     // + one scratch word per warp
+      int f_ctas = 0;
+      if (fsmem <= kFlightSmemMax) {
+        e = flights_prepare(nw, fsmem, &f_ctas);
+        if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights attributes");
+      }
+      if (g_ctx.engine == 2 && f_ctas < 1) {
+        set_error("engine 2: the touched region %dx%d of a flight does not fit %zu B of shared memory", bw, bh, kFlightSmemMax);
+        return UQS_ERR_BAD_ARG;
+      }
+      // auto: resident when several CTAs fit an SM (barrier stalls of one hide behind the others) and there is at
+      // least a flight per SM (measured crossover); otherwise the sub-tile engine (time-sliced when flights are few)
+      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || (f_ctas >= 2 && nf >= g_ctx.sm_count));
+      if (resident) {
+        FlightArgs FA;
+        FA.frames = (const uint4*)g_ctx.w->frames.p;
+        FA.rays = (const uint2*)g_ctx.w->rays.p;
+        FA.boxes = (const int4*)g_ctx.w->boxes.p;
+        FA.grids = grids + (size_t)f0 * dp.W * dp.H;
+        FA.job_counter = counters + 8;
+        FA.n_flights = nf; FA.n_frames = n_frames;
+        FA.W = dp.W; FA.H = dp.H; FA.pitch = fpitch; FA.max_rows = bh; FA.ring_size = ring_size;
+        FA.lo_free = dp.lo_free; FA.lo_occ = dp.lo_occ; FA.lo_min = dp.lo_min; FA.lo_max = dp.lo_max;
+        FA.end_nohit = dp.end_nohit;
+        FA.accumulate = accumulate;
+        e = cudaMemsetAsync(FA.job_counter, 0, sizeof(unsigned long long), st);
+        // cells outside a flight's box are never touched: they are zero in a fresh replay
+        if (e == cudaSuccess && !accumulate) e = cudaMemsetAsync(FA.grids, 0, (size_t)nf * dp.W * dp.H, st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset before k_replay_flights");
+        const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)f_ctas * g_ctx.sm_count);
+        KernelTimer t_rep(2);
+        e = flights_launch(nw, fgrid, fsmem, st, FA);
+        t_rep.stop();
+        if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights launch");
+        g_ctx.launches += 2;
+        continue;
+      }
     }
     // sub-tiles nearest the grid centre first (trajectories stay within 60 % of the half-extent,
     // so those are the heavy ones); cached per geometry
@@ -465,8 +488,8 @@ int uqs_set_tuning(int sw, int sh, int time_slices) {
 }
 
 int uqs_set_engine(int engine, int flight_warps) {
-  if (engine < 0 || engine > 2 || (flight_warps != 0 && flight_warps != 8 && flight_warps != 16 && flight_warps != 32)) {
-    set_error("engine must be 0 (auto), 1 (sub-tiles) or 2 (grid resident); warps 0, 8, 16 or 32");
+  if (engine < 0 || engine > 2 || (flight_warps != 0 && flight_warps != 4 && flight_warps != 8 && flight_warps != 16 && flight_warps != 32)) {
+    set_error("engine must be 0 (auto), 1 (sub-tiles) or 2 (grid resident); warps 0, 4, 8, 16 or 32");
     return UQS_ERR_BAD_ARG;
   }
   g_ctx.engine = engine;

@@ -21,11 +21,11 @@ struct DevBuf {
 // scratch of one in-flight replay: ray/frame records, counters, P0 increments (+ an optional
 // stream override, used by the host-buffer pipeline to keep two chunks' kernels in flight)
 struct Work {
-  DevBuf rays, frames, groups, counters, inc, scan, order, maps;
+  DevBuf rays, frames, groups, counters, inc, scan, order, maps, boxes;
   int order_nsx = 0, order_nsy = 0;             // geometry the cached tile order was built for
   cudaStream_t stream = nullptr;
   void release() {
-    DevBuf* all[] = { &rays, &frames, &groups, &counters, &inc, &scan, &order, &maps };
+    DevBuf* all[] = { &rays, &frames, &groups, &counters, &inc, &scan, &order, &maps, &boxes };
     order_nsx = order_nsy = 0;
     for (DevBuf* b : all) b->release();
   }

@@ -261,19 +261,44 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
       float ra, rb;
       if (xmaj) { ra = xpos ? (ypos ? 0.f : 8.f) : 4.f; rb = (xpos == ypos) ? 1.f : -1.f; }
       else      { ra = ypos ? 2.f : 6.f;                rb = (xpos == ypos) ? -1.f : 1.f; }
-      const float sigma = (m > 0) ? ra + rb * ((float)n / (float)m) : 0.f;
+      float sigma = (m > 0) ? ra + rb * ((float)n / (float)m) : 0.f;
+      if (sigma >= 8.f) sigma -= 8.f;
+      const int mmax = __reduce_max_sync(0xffffffffu, m);
+      const unsigned any = __ballot_sync(0xffffffffu, m >= 0);
+      const unsigned dir = __ballot_sync(0xffffffffu, m >= 1);     // beams that have a direction
+      // Fast path: beams are issued in angular order, so their ring coordinates are normally sorted and the
+      // closest pair is a pair of neighbours.  Dropping the per-pair length cap only enlarges the bound.
+      const unsigned above = dir & ~(0xffffffffu >> (31 - lane));
+      const int nxt = above ? (__ffs(above) - 1) : (__ffs(dir) - 1);
+      const float sn = __shfl_sync(0xffffffffu, sigma, nxt & 31);
+      const bool has_dir = m >= 1;
+      float gap = sn - sigma;                                           // to the next beam, cyclically
+      const bool wraps = has_dir && gap < 0.f;
+      if (wraps) gap += 8.f;
+      // circularly sorted <=> the cyclic sequence passes 8 -> 0 at most once
+      const bool sorted = __popc(__ballot_sync(0xffffffffu, wraps)) <= 1;
+      if (__popc(any) >= 2) {
+        if (sorted || __popc(dir) < 2) {
+          int kk = 1;                                                   // the start cell is shared by all beams
+          if (has_dir && __popc(dir) >= 2) kk = (gap > 1e-4f) ? (int)(1.0f / (gap - 2e-5f)) + 2 : 0x7fffffff;
+          k0 = min(__reduce_max_sync(0xffffffffu, kk), mmax + 1);
+        } else {
+          // beams out of angular order (very short rays quantise coarsely): exact all-pairs bound
 #pragma unroll 4
-      for (int j = 1; j <= 16; j++) {
-        const int pl = (lane + j) & 31;
-        const float sp = __shfl_sync(0xffffffffu, sigma, pl);
-        const int mp = __shfl_sync(0xffffffffu, m, pl);
-        float dlt = fabsf(sigma - sp);
-        dlt = fminf(dlt, 8.f - dlt);
-        int kk = (dlt > 1e-4f) ? (int)(1.0f / (dlt - 2e-5f)) + 2 : 0x7fffffff;
-        kk = min(kk, min(m, mp) + 1);          // a beam has no step beyond its own length
-        if (m >= 0 && mp >= 0) k0 = max(k0, kk);
+          for (int j = 1; j <= 16; j++) {
+            const int pl = (lane + j) & 31;
+            const float sp = __shfl_sync(0xffffffffu, sigma, pl);
+            const int mp = __shfl_sync(0xffffffffu, m, pl);
+            float dlt = fabsf(sigma - sp);
+            dlt = fminf(dlt, 8.f - dlt);
+            int kk = (dlt > 1e-4f) ? (int)(1.0f / (dlt - 2e-5f)) + 2 : 0x7fffffff;
+            if (m < 1 || mp < 1) kk = 1;
+            kk = min(kk, min(m, mp) + 1);          // a beam has no step beyond its own length
+            if (m >= 0 && mp >= 0) k0 = max(k0, kk);
+          }
+          k0 = __reduce_max_sync(0xffffffffu, k0);
+        }
       }
-      k0 = __reduce_max_sync(0xffffffffu, k0);
     }
 
     xmin = __reduce_min_sync(0xffffffffu, xmin);
@@ -649,7 +674,7 @@ struct Beam {
   int k0;           // shared-step bound of the frame
 };
 
-__device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int lo_occ, int end_nohit) {
+__device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int bx0, int by0, int lo_occ, int end_nohit) {
   Beam b;
   const int dx = sext12(rec.x), dy = sext12(rec.x >> 12);
   const int adx = abs(dx), ady = abs(dy);
@@ -664,7 +689,7 @@ __device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int lo_
   if (xmaj) { b.ra = xpos ? (ypos ? 0 : 8) : 4; b.rb = (xpos == ypos) ? 1 : -1; }
   else      { b.ra = ypos ? 2 : 6;              b.rb = (xpos == ypos) ? -1 : 1; }
   b.end_delta = (rec.x & kRayHit) ? lo_occ : end_nohit;
-  b.base = (int)(org.y & 0xffffu) * P + (int)(org.x & 0xffffu);
+  b.base = ((int)(org.y & 0xffffu) - by0) * P + ((int)(org.x & 0xffffu) - bx0);
   b.k0 = (int)(org.x >> 16);
   return b;
 }
@@ -677,41 +702,50 @@ __device__ __forceinline__ void rmw_cell(int8_t* cell, int delta, int lo_min, in
 }
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 8 : ((NW <= 8) ? 4 : ((NW <= 16) ? 2 : 1)))
 k_replay_flights(FlightArgs A) {
   int8_t* grid_s = reinterpret_cast<int8_t*>(uqs_smem);
   __shared__ int s_flight;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int P = A.pitch;
-  const int words = (P * A.H) >> 2;
   // per-warp collision table, indexed by the position of a cell on the max-norm ring of
   // radius k (all step-k cells of a frame lie on that ring; the map cell -> position is injective)
-  uint8_t* ring = reinterpret_cast<uint8_t*>(uqs_smem) + (size_t)P * A.H + (size_t)w * A.ring_size;
+  uint8_t* ring = reinterpret_cast<uint8_t*>(uqs_smem) + (size_t)P * A.max_rows + (size_t)w * A.ring_size;
   const int ring_mask = A.ring_size - 1;
+  const uint32_t grid_sa = (uint32_t)__cvta_generic_to_shared(grid_s);
+  // scratch byte per warp for lanes that have nothing to update (after the collision tables)
+  const uint32_t dummy_sa = grid_sa + (uint32_t)(P * A.max_rows + NW * A.ring_size + 4 * w);
+  const int lo_free = A.lo_free, lo_min = A.lo_min, lo_max = A.lo_max;
+  const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
 
   for (;;) {
     if (threadIdx.x == 0) s_flight = (int)atomicAdd(A.job_counter, 1ull);
     __syncthreads();
     const int flight = s_flight;
     if (flight >= A.n_flights) break;
-    int8_t* grid_g = A.grids + (size_t)flight * A.W * A.H;
-    const bool vec = ((A.W & 3) == 0) && ((reinterpret_cast<size_t>(grid_g) & 3) == 0);
+    // only the bounding box of the cells this flight can touch is kept resident (k_flight_boxes);
+    // everything outside keeps its value in HBM (zero unless accumulating)
+    const int4 box = A.boxes[flight];
+    const int bx0 = box.x, by0 = box.y, bw = box.z - box.x, bh = box.w - box.y;
+    if (bw <= 0 || bh <= 0) { __syncthreads(); continue; }
+    int8_t* grid_g = A.grids + (size_t)flight * A.W * A.H + (size_t)by0 * A.W + bx0;
+    const bool vec = (((A.W | bx0 | bw) & 3) == 0) && ((reinterpret_cast<size_t>(grid_g) & 3) == 0);
 
     if (A.accumulate) {
       if (vec) {
-        const int wpr = A.W >> 2;
-        for (int i = threadIdx.x; i < wpr * A.H; i += NW * 32) {
+        const int wpr = bw >> 2;
+        for (int i = threadIdx.x; i < wpr * bh; i += NW * 32) {
           const int r = i / wpr, c = i - r * wpr;
           reinterpret_cast<uint32_t*>(grid_s + r * P)[c] = reinterpret_cast<const uint32_t*>(grid_g + (size_t)r * A.W)[c];
         }
       } else {
-        for (int i = threadIdx.x; i < A.W * A.H; i += NW * 32) {
-          const int r = i / A.W, c = i - r * A.W;
+        for (int i = threadIdx.x; i < bw * bh; i += NW * 32) {
+          const int r = i / bw, c = i - r * bw;
           grid_s[r * P + c] = grid_g[(size_t)r * A.W + c];
         }
       }
     } else {
-      for (int i = threadIdx.x; i < words; i += NW * 32) reinterpret_cast<uint32_t*>(grid_s)[i] = 0u;
+      for (int i = threadIdx.x; i < ((P * bh) >> 2); i += NW * 32) reinterpret_cast<uint32_t*>(grid_s)[i] = 0u;
     }
     __syncthreads();
 
@@ -723,12 +757,14 @@ k_replay_flights(FlightArgs A) {
       rec_n = __ldg(&rays[32 + lane]);
       org_n = __ldg(reinterpret_cast<const uint2*>(&frames[1]));
     }
-    Beam B = decode_beam(__ldg(&rays[lane]), __ldg(reinterpret_cast<const uint2*>(&frames[0])), P, A.lo_occ, A.end_nohit);
+    Beam B = decode_beam(__ldg(&rays[lane]), __ldg(reinterpret_cast<const uint2*>(&frames[0])), P, bx0, by0, A.lo_occ, A.end_nohit);
+#pragma unroll 2
     for (int f = 0; f < A.n_frames; f++) {
       const uint2 rec1 = rec_n, org1 = org_n;
-      if (f + 2 < A.n_frames) {
-        rec_n = __ldg(&rays[(size_t)(f + 2) * 32 + lane]);
-        org_n = __ldg(reinterpret_cast<const uint2*>(&frames[f + 2]));
+      {   // unconditional (clamped) so that the loads land straight in the rotating registers
+        const int fn = min(f + 2, A.n_frames - 1);
+        rec_n = __ldg(&rays[(size_t)fn * 32 + lane]);
+        org_n = __ldg(reinterpret_cast<const uint2*>(&frames[fn]));
       }
       const int m = B.m, n2 = B.n2, h2 = B.m & ~1, sM = B.sM, sN = B.sN, base = B.base;
       const uint32_t inv = B.inv;
@@ -740,7 +776,7 @@ k_replay_flights(FlightArgs A) {
         const bool act = k <= m;
         const int q = minor_steps(k, n2, h2, inv);
         const int addr = base + k * sM + q * sN;
-        const int delta = (k == m) ? B.end_delta : -A.lo_free;
+        const int delta = (k == m) ? B.end_delta : -lo_free;
         // runs of consecutive lanes on one cell (beams are ordered by angle, so nearly all
         // collisions are between neighbours); only the head of a run enters the ring table
         const unsigned key = act ? (unsigned)addr : (0x80000000u | (unsigned)lane);
@@ -750,14 +786,15 @@ k_replay_flights(FlightArgs A) {
         int pos = B.ra * k + B.rb * q;
         if (pos == 8 * k) pos = 0;
         const int slot = pos & ring_mask;
-        if (head) ring[slot] = (uint8_t)lane;
+        if (head) sts_u8(ring_sa + (uint32_t)slot, lane);
         __syncwarp();
-        const bool lost = head && ring[slot] != (uint8_t)lane;
+        const bool lost = head && lds_s8(ring_sa + (uint32_t)slot) != lane;
         const unsigned boundm = __ballot_sync(0xffffffffu, bound);
         const unsigned actm = __ballot_sync(0xffffffffu, act);
         unsigned pend = __ballot_sync(0xffffffffu, lost);
+        const uint32_t cell = grid_sa + (uint32_t)addr;
         if ((boundm & actm) == actm && pend == 0u) {
-          if (act) rmw_cell(grid_s + addr, delta, A.lo_min, A.lo_max);
+          if (act) sts_u8(cell, min(max(lds_s8(cell) + delta, lo_min), lo_max));
         } else {
           const unsigned upto = 0xffffffffu >> (31 - lane);               // lanes 0..lane
           const int start = 31 - __clz(boundm & upto);
@@ -775,54 +812,54 @@ k_replay_flights(FlightArgs A) {
           const bool uniform = (peers & endm) == 0u;          // only free-space steps in this cell
           if (act && uniform && lane == __ffs(peers) - 1) {
             // repeated clamp(v - free) == max(v - cnt*free, lo_min)
-            const int v = (int)grid_s[addr] - __popc(peers) * A.lo_free;
-            grid_s[addr] = (int8_t)max(v, A.lo_min);
+            sts_u8(cell, max(lds_s8(cell) - __popc(peers) * lo_free, lo_min));
           }
           const bool mixed = act && !uniform;
           const int rank = __popc(peers & ((1u << lane) - 1u));
           const int rounds = __reduce_max_sync(0xffffffffu, mixed ? rank : -1);
           for (int r = 0; r <= rounds; r++) {
-            if (mixed && rank == r) rmw_cell(grid_s + addr, delta, A.lo_min, A.lo_max);
+            if (mixed && rank == r) sts_u8(cell, min(max(lds_s8(cell) + delta, lo_min), lo_max));
             __syncwarp();
           }
         }
         __syncwarp();      // ring[] is rewritten by the next step
       }
 
-      // ---- steps k >= K0: every cell is touched by one beam only; four steps in flight -------------
+      // ---- steps k >= K0: every cell is touched by one beam only; four steps in flight, branch-free
+      // (lanes past their beam's end read-modify-write a scratch byte behind the resident region)
       int k = w + ((max(B.k0 - w, 0) + NW - 1) / NW) * NW;
+      const uint32_t gbase = grid_sa + (uint32_t)base;
+      const int free_delta = -lo_free;
       for (; k <= mmax; k += 4 * NW) {
-        int addr[4], val[4];
+        uint32_t addr[4];
+        int val[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int ku = k + u * NW;
-          addr[u] = base + ku * sM + minor_steps(ku, n2, h2, inv) * sN;
+          const uint32_t a = gbase + (uint32_t)(ku * sM + minor_steps(ku, n2, h2, inv) * sN);
+          addr[u] = (ku <= m) ? a : dummy_sa;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (k + u * NW <= m) val[u] = (int)grid_s[addr[u]];
+        for (int u = 0; u < 4; u++) val[u] = lds_s8(addr[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const int ku = k + u * NW;
-          if (ku <= m) {
-            const int v = val[u] + ((ku == m) ? B.end_delta : -A.lo_free);
-            grid_s[addr[u]] = (int8_t)min(max(v, A.lo_min), A.lo_max);
-          }
+          const int v = val[u] + ((k + u * NW == m) ? B.end_delta : free_delta);
+          sts_u8(addr[u], min(max(v, lo_min), lo_max));
         }
       }
-      B = decode_beam(rec1, org1, P, A.lo_occ, A.end_nohit);    // frame f+1, independent of the grid
+      B = decode_beam(rec1, org1, P, bx0, by0, A.lo_occ, A.end_nohit);    // frame f+1, independent of the grid
       __syncthreads();
     }
 
     if (vec) {
-      const int wpr = A.W >> 2;
-      for (int i = threadIdx.x; i < wpr * A.H; i += NW * 32) {
+      const int wpr = bw >> 2;
+      for (int i = threadIdx.x; i < wpr * bh; i += NW * 32) {
         const int r = i / wpr, c = i - r * wpr;
         reinterpret_cast<uint32_t*>(grid_g + (size_t)r * A.W)[c] = reinterpret_cast<const uint32_t*>(grid_s + r * P)[c];
       }
     } else {
-      for (int i = threadIdx.x; i < A.W * A.H; i += NW * 32) {
-        const int r = i / A.W, c = i - r * A.W;
+      for (int i = threadIdx.x; i < bw * bh; i += NW * 32) {
+        const int r = i / bw, c = i - r * bw;
         grid_g[(size_t)r * A.W + c] = grid_s[r * P + c];
       }
     }
@@ -830,8 +867,42 @@ k_replay_flights(FlightArgs A) {
   }
 }
 
+// Bounding box of every cell a flight can touch = union of its 32-frame group boxes; x is widened to
+// multiples of 4 (when W allows) so that rows move as 32-bit words.  dims[0..1] = max width / height.
+__global__ void k_flight_boxes(int n_flights, int groups_per_flight, const uint2* __restrict__ groups, int W, int H,
+                               int4* __restrict__ boxes, int* __restrict__ dims) {
+  const int flight = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (flight >= n_flights) return;
+  int x0 = 0x7fff, x1 = -1, y0 = 0x7fff, y1 = -1;
+  for (int g = lane; g < groups_per_flight; g += 32) {
+    const uint2 b = __ldg(&groups[(size_t)flight * groups_per_flight + g]);
+    const int bx0 = (int)(b.x & 0xffffu), bx1 = (int)(b.x >> 16), by0 = (int)(b.y & 0xffffu), by1 = (int)(b.y >> 16);
+    if (bx0 <= bx1 && by0 <= by1) { x0 = min(x0, bx0); x1 = max(x1, bx1); y0 = min(y0, by0); y1 = max(y1, by1); }
+  }
+  x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+  y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+  if (lane == 0) {
+    int4 box = make_int4(0, 0, 0, 0);
+    if (x0 <= x1 && y0 <= y1) {
+      x1 += 1; y1 += 1;                                  // exclusive
+      if ((W & 3) == 0) { x0 &= ~3; x1 = min((x1 + 3) & ~3, W); }
+      box = make_int4(x0, y0, x1, y1);
+      atomicMax(&dims[0], x1 - x0);
+      atomicMax(&dims[1], y1 - y0);
+    }
+    boxes[flight] = box;
+  }
+}
+
 static void (*flight_kernel(int nw))(FlightArgs) {
-  return nw == 8 ? k_replay_flights<8> : (nw == 32 ? k_replay_flights<32> : k_replay_flights<16>);
+  return nw == 4 ? k_replay_flights<4> : (nw == 8 ? k_replay_flights<8> : (nw == 32 ? k_replay_flights<32> : k_replay_flights<16>));
+}
+
+cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint2* groups, int W, int H, int4* boxes,
+                                int* dims, cudaStream_t st) {
+  k_flight_boxes<<<(unsigned)((n_flights + 3) / 4), 128, 0, st>>>(n_flights, groups_per_flight, groups, W, H, boxes, dims);
+  return cudaGetLastError();
 }
 
 cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm) {

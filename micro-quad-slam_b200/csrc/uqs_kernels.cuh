@@ -36,7 +36,9 @@ struct FlightArgs {
   int8_t* grids;
   unsigned long long* job_counter;
   int n_flights, n_frames;
+  const int4* boxes;        // per flight: resident cell range [x0,x1) x [y0,y1)
   int W, H, pitch;
+  int max_rows;             // rows of the resident region (max over the launch's flights)
   int ring_size;            // bytes of collision table per warp (power of two), placed after the grid
   int lo_free, lo_occ, lo_min, lo_max, end_nohit;
   int accumulate;
@@ -68,6 +70,8 @@ __global__ void k_world_to_grid_one(DevParams p, float wx, float wy, int* out);
 __global__ void k_replay_tiles(ReplayArgs A);
 __global__ void k_compose_slices(int8_t* grids, const uint32_t* maps, int n_flights, int W, int H, int S, int row0,
                                  int rows);
+cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint2* groups, int W, int H, int4* boxes,
+                                int* dims, cudaStream_t st);
 cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm);
 cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);

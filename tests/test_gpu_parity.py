@@ -11,10 +11,10 @@ from conftest import first_diff, have_ref
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tiles", "resident8", "resident16", "resident32"])
+@pytest.fixture(params=["tiles", "resident4", "resident8", "resident16", "resident32"])
 def engine(request, gpu):
     """Both replay engines (and the resident engine's warp counts) must give identical bytes."""
-    e, nw = {"tiles": (1, 0), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[request.param]
+    e, nw = {"tiles": (1, 0), "resident4": (2, 4), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[request.param]
     gpu.set_engine(e, nw)
     yield request.param
     gpu.set_engine(0, 0)

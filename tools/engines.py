@@ -8,7 +8,7 @@ for nf in [int(a) for a in sys.argv[1:]] or [1184]:
     w = syn.scaled(syn.CONFIGS["c3"], n_flights=nf); d = syn.generate(w); p = w.params()
     tx, ty, tyaw, tr = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (d["x_true"], d["y_true"], d["frame_yaw_deg"], d["ranges"]))
     g = torch.zeros((w.n_flights, p.H, p.W), dtype=torch.int8, device=dev)
-    for eng, nw in [(1,0),(2,8),(2,16),(2,32)]:
+    for eng, nw in [(1,0),(2,4),(2,8),(2,16)]:
         m.set_engine(eng, nw)
         st = m.replay_dev(p, w.n_flights, w.n_frames, tx.data_ptr(), ty.data_ptr(), tyaw.data_ptr(), tr.data_ptr(), g.data_ptr(), want_stats=True)
         best=1e9
