@@ -188,6 +188,32 @@ def test_ragged_and_degenerate_logs(gpu, oracle, synth, engine):
         assert st["ray_cell_updates"] == U
 
 
+def test_flight_without_any_return_stays_untouched(gpu, oracle, synth, engine):
+    """a member whose every range is NaN touches nothing: zero grid in a fresh replay, unchanged when accumulating"""
+    import torch
+    w = synth.scaled(synth.CONFIGS["c3"], n_flights=3, n_samples=300)
+    d = synth.generate(w)
+    p = w.params()
+    d["ranges"][1] = np.nan
+    got, st = gpu.replay(p, d["x_true"], d["y_true"], d["frame_yaw_deg"], d["ranges"])
+    want, U = oracle_grids(oracle, p, d)
+    assert np.array_equal(got, want) and not got[1].any() and st["ray_cell_updates"] == U
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (d["x_true"], d["y_true"], d["frame_yaw_deg"], d["ranges"])]
+    g = torch.full((3, p.H, p.W), 17, dtype=torch.int8, device=dev)
+    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        gpu.replay_dev(p, 3, 300, *(a.data_ptr() for a in t), g.data_ptr(), accumulate=True)
+        torch.cuda.synchronize()
+    finally:
+        gpu.set_stream(None)
+    out = g.cpu().numpy()
+    assert (out[1] == 17).all() and (out[0] != 17).any()
+    start = np.full((p.H, p.W), 17, np.int8)
+    ref0, _ = oracle.replay(p, d["x_true"][0], d["y_true"][0], d["frame_yaw_deg"][0], d["ranges"][0], grid=start)
+    assert np.array_equal(out[0], ref0)
+
+
 def test_saturation_hazards_hover(gpu, oracle, engine):
     """a hovering drone next to a wall drives cells into both clamps with interleaved +6 / -1:
     the order-sensitive case of SURVEY 0.4 (accumulate-then-clamp gets these cells wrong)."""
