@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--cpu-flights-per-core", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 sub-tiles, 2 resident (tuning experiments)")
+    ap.add_argument("--flight-warps", type=int, default=0, help="warps per resident CTA (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -271,6 +273,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     m.init(local)                                   # fails loudly if the CUDA library cannot run
     m.set_stream(torch.cuda.current_stream().cuda_stream)
+    m.set_engine(args.engine, args.flight_warps)
 
     w = pick_workload(synth, args.workload, args.flights)
     p = w.params()

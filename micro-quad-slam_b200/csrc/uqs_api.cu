@@ -161,8 +161,10 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   // Engine 2 keeps, per CTA, the bounding box of the cells one flight can touch resident in shared memory
   // (frame-synchronous).  Whether it fits -- and how many CTAs share an SM -- is only known
   // after the ray set-up of a chunk (k_flight_boxes), so the choice is made per chunk below.
-  // warps per resident CTA: 8 when there are flights for every CTA slot, 16 when flights are scarce
-  const int nw = g_ctx.flight_warps ? g_ctx.flight_warps : (n_flights >= 4 * g_ctx.sm_count ? 8 : 16);
+  // warps per resident CTA (measured): 4 when there are flights for every CTA slot of every SM -- per-frame
+  // bookkeeping is paid per warp -- more warps per CTA when flights are scarce
+  const int nw = g_ctx.flight_warps ? g_ctx.flight_warps
+                                    : (n_flights >= 4 * g_ctx.sm_count ? 4 : (n_flights >= 2 * g_ctx.sm_count ? 8 : 16));
   const bool may_reside = g_ctx.engine != 1 && row0 == 0 && rows == dp.H;
   if (g_ctx.engine == 2 && !may_reside) {
     set_error("engine 2 (resident) cannot replay a row band");
@@ -224,8 +226,9 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       if (((fpitch >> 2) & 1) == 0) fpitch += 4;
       int ring_size = 256;                                  // per-warp collision table (power of two)
       const size_t region = (size_t)fpitch * bh;
-      while (ring_size > 32 && region + (size_t)(ring_size + 4) * nw > kFlightSmemMax) ring_size >>= 1;
-      const size_t fsmem = region + (size_t)(ring_size + 4) * nw;     // + one scratch word per warp
+      const size_t dec_bytes = (size_t)nw * kDecSlotBytes + 16;      // ring of decoded frames (+ alignment)
+      while (ring_size > 32 && region + (size_t)(ring_size + 4) * nw + dec_bytes > kFlightSmemMax) ring_size >>= 1;
+      const size_t fsmem = region + (size_t)(ring_size + 4) * nw + dec_bytes;     // + one scratch word per warp
       int f_ctas = 0;
       if (fsmem <= kFlightSmemMax) {
         e = flights_prepare(nw, fsmem, &f_ctas);

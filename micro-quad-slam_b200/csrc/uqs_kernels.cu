@@ -406,6 +406,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 // pin a kernel parameter in a register (otherwise it is re-read from the constant bank in inner loops)
 __device__ __forceinline__ int in_reg(int v) {
   asm volatile("" : "+r"(v));
@@ -717,6 +725,8 @@ k_replay_flights(FlightArgs A) {
   const uint32_t dummy_sa = grid_sa + (uint32_t)(P * A.max_rows + NW * A.ring_size + 4 * w);
   const int lo_free = A.lo_free, lo_min = A.lo_min, lo_max = A.lo_max;
   const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
+  // ring of decoded frames (16-byte aligned, after the scratch words)
+  const uint32_t dec_sa = (grid_sa + (uint32_t)(P * A.max_rows + NW * A.ring_size + 4 * NW) + 15u) & ~15u;
 
   for (;;) {
     if (threadIdx.x == 0) s_flight = (int)atomicAdd(A.job_counter, 1ull);
@@ -751,24 +761,42 @@ k_replay_flights(FlightArgs A) {
 
     const uint4* frames = A.frames + (size_t)flight * A.n_frames;
     const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
-    // two frames of records in flight; beam decode of frame f+1 is issued before the barrier of frame f
-    uint2 rec_n = make_uint2(0u, 0u), org_n = make_uint2(0u, 0u);
-    if (A.n_frames > 1) {
-      rec_n = __ldg(&rays[32 + lane]);
-      org_n = __ldg(reinterpret_cast<const uint2*>(&frames[1]));
+    // Beam decode is shared: warp (f mod NW) decodes frame f + NW/2 into a ring of NW slots in shared memory
+    // (32 lanes x 16 B + one frame word per slot); every warp then reads its lane's 16 B per frame.  A warp
+    // therefore decodes -- and loads raw records for -- only every NW-th frame, one turn ahead.
+    constexpr int L = NW / 2;
+    auto decode_store = [&](uint2 rec, uint2 org, int slot) {
+      const Beam b = decode_beam(rec, org, P, bx0, by0, A.lo_occ, A.end_nohit);
+      const int mx = __reduce_max_sync(0xffffffffu, b.m);
+      const uint32_t at = dec_sa + (uint32_t)slot * kDecSlotBytes;
+      sts_v4(at + 16u * (uint32_t)lane, b.inv, (uint32_t)b.n2 | ((uint32_t)(b.m + 1) << 16),
+             ((uint32_t)b.sM & 0xffffu) | ((uint32_t)b.sN << 16),
+             ((uint32_t)b.end_delta & 0xffu) | ((uint32_t)b.ra << 8) | (b.rb < 0 ? 0x1000u : 0u));
+      if (lane == 0) sts_v4(at + 512u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, 0u);
+    };
+    if (w < L && w < A.n_frames)
+      decode_store(__ldg(&rays[(size_t)w * 32 + lane]), __ldg(reinterpret_cast<const uint2*>(&frames[w])), w);
+    // raw records of this warp's next turn (frame w + L), loaded one turn (NW frames) ahead
+    uint2 raw_rec, raw_org;
+    {
+      const int g = min(w + L, A.n_frames - 1);
+      raw_rec = __ldg(&rays[(size_t)g * 32 + lane]);
+      raw_org = __ldg(reinterpret_cast<const uint2*>(&frames[g]));
     }
-    Beam B = decode_beam(__ldg(&rays[lane]), __ldg(reinterpret_cast<const uint2*>(&frames[0])), P, bx0, by0, A.lo_occ, A.end_nohit);
-#pragma unroll 2
+    __syncthreads();
     for (int f = 0; f < A.n_frames; f++) {
-      const uint2 rec1 = rec_n, org1 = org_n;
-      {   // unconditional (clamped) so that the loads land straight in the rotating registers
-        const int fn = min(f + 2, A.n_frames - 1);
-        rec_n = __ldg(&rays[(size_t)fn * 32 + lane]);
-        org_n = __ldg(reinterpret_cast<const uint2*>(&frames[fn]));
-      }
-      const int m = B.m, n2 = B.n2, h2 = B.m & ~1, sM = B.sM, sN = B.sN, base = B.base;
-      const uint32_t inv = B.inv;
-      const int mmax = __reduce_max_sync(0xffffffffu, m);
+      const uint32_t at = dec_sa + (uint32_t)(f & (NW - 1)) * kDecSlotBytes;
+      const uint4 dv = lds_v4(at + 16u * (uint32_t)lane);
+      const uint4 fv = lds_v4(at + 512u);
+      const uint32_t inv = dv.x;
+      const int n2 = (int)(dv.y & 0xffffu), m = (int)(dv.y >> 16) - 1, h2 = m & ~1;
+      const int sM = (int)(short)(dv.z & 0xffffu), sN = (int)dv.z >> 16;
+      Beam B;
+      B.end_delta = (int)(signed char)(dv.w & 0xffu);
+      B.ra = (int)((dv.w >> 8) & 0xfu);
+      B.rb = (dv.w & 0x1000u) ? -1 : 1;
+      B.k0 = (int)fv.y;
+      const int base = (int)fv.x, mmax = (int)fv.z;
       const int kshared = min(B.k0, mmax + 1);
 
       // ---- steps k < K0: beams may meet in a cell; detect and keep beam order --------------------
@@ -847,7 +875,13 @@ k_replay_flights(FlightArgs A) {
           sts_u8(addr[u], min(max(v, lo_min), lo_max));
         }
       }
-      B = decode_beam(rec1, org1, P, bx0, by0, A.lo_occ, A.end_nohit);    // frame f+1, independent of the grid
+      if ((f & (NW - 1)) == w) {                    // this warp's turn: decode frame f + L, prefetch its next turn
+        const int g = f + L;
+        if (g < A.n_frames) decode_store(raw_rec, raw_org, g & (NW - 1));
+        const int gn = min(g + NW, A.n_frames - 1);
+        raw_rec = __ldg(&rays[(size_t)gn * 32 + lane]);
+        raw_org = __ldg(reinterpret_cast<const uint2*>(&frames[gn]));
+      }
       __syncthreads();
     }
 
