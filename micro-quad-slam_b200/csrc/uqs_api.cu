@@ -94,6 +94,12 @@ int make_dev_params(const uqs_params* p, DevParams* d) {
   d->hit_below = mr - hm;
   d->half_fov = fov * 0.5f;
   d->deg2rad = pi_f / 180.0f;
+  for (int c = 0; c < 8; c++) {                       // (:295-296) one rounding per operator, like the reference
+    volatile float cf = (float)c;
+    volatile float u = (cf - 3.5f) / 3.5f;
+    volatile float hf = d->half_fov;
+    d->col_off[c] = u * hf;
+  }
   d->lo_free = p->lo_free; d->lo_occ = p->lo_occ; d->lo_min = p->lo_min; d->lo_max = p->lo_max;
   d->end_nohit = -(p->lo_free / 2);
   return UQS_OK;

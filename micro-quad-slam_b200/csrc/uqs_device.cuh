@@ -16,6 +16,7 @@ struct DevParams {
   float res, ox, oy;
   float max_range, min_range, hit_below;  // hit_below = max_range - hit_margin (uav_local_nav.c:292)
   float half_fov;                         // fov * 0.5f                          (:284)
+  float col_off[8];                       // ((float)c - 3.5f) / 3.5f * half_fov (:295-296), folded on the host in binary32
   float deg2rad;                          // (float)M_PI / 180.0f                (:299)
   int   lo_free, lo_occ, lo_min, lo_max;
   int   end_nohit;                        // -(lo_free / 2), integer division   (:266)
@@ -79,6 +80,7 @@ __device__ __forceinline__ bool sincosf_glibc(float y, float& sn, float& cs) {
 // (int)lrintf(q): x86-64 cvtss2si yields 0x8000000000000000 for NaN and |q| >= 2^63,
 // whose low 32 bits are 0; in range the cast keeps the low 32 bits.
 __device__ __forceinline__ int lrintf_as_int(float q) {
+  if (fabsf(q) < 2147483520.0f) return __float2int_rn(q);          // fits int32: same value, 32-bit convert
   const long long r = (fabsf(q) < 9223372036854775808.0f) ? __float2ll_rn(q)
                                                           : (long long)0x8000000000000000ull;
   return (int)r;
@@ -106,8 +108,7 @@ __device__ __forceinline__ int beam_endpoint(const DevParams& p, float px, float
   if (dist > p.max_range) dist = p.max_range;
   const int d = b >> 3, c = b & 7;
   const float centre = (d == 0) ? 0.0f : (d == 1) ? 90.0f : (d == 2) ? 180.0f : -90.0f;
-  const float u = __fdiv_rn(__fsub_rn((float)c, 3.5f), 3.5f);
-  const float off = __fmul_rn(u, p.half_fov);
+  const float off = p.col_off[c];
   const float ang_deg = __fadd_rn(__fadd_rn(yaw_deg, centre), off);
   const float ang = __fmul_rn(ang_deg, p.deg2rad);
   float sn, cs;

@@ -234,7 +234,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
         } else {
           w0 = ((uint32_t)dx & 0xfffu) | (((uint32_t)dy & 0xfffu) << 12) | (hit ? kRayHit : 0u) |
                kRayValid;
-          w1 = m ? (uint32_t)(((1ull << 31) + (unsigned)m - 1) / (unsigned)m) : 0u;
+          w1 = m ? (0x7fffffffu / (unsigned)m + 1u) : 0u;      // ceil(2^31 / m) in 32-bit arithmetic
           xmin = min(gx0, gx1); xmax = max(gx0, gx1);
           ymin = min(gy0, gy1); ymax = max(gy0, gy1);
           cells = (unsigned long long)m + 1;

@@ -6,6 +6,7 @@
 // Copies overlap only from page-locked host memory (cudaHostRegister / cudaHostAlloc / torch
 // pin_memory); pageable buffers still work, serialised by the driver.
 #include <algorithm>
+#include <vector>
 
 #include "uqs_host.h"
 
@@ -72,15 +73,20 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   if (rc) return rc;
   const bool flow = L.t_ms != nullptr;
   const size_t cells = (size_t)p->W * p->H;
-  // chunk: the sub-tile engine wants >= ~8 flights per SM per launch to keep its tail short, so cut
-  // into at most 8 chunks of at least that size; fewer flights than two such chunks go in one piece
-  const int min_chunk = 8 * g_ctx.sm_count;
-  int n_want = std::max(1, std::min(8, n_flights / min_chunk));
-  if ((size_t)n_flights * n_frames * 152 > ((size_t)6 << 30))           // bound the staging buffers (2 x chunk)
-    n_want = std::max<int>(n_want, (int)(((size_t)n_flights * n_frames * 152) / ((size_t)3 << 30)) + 1);
-  int chunk = (n_flights + n_want - 1) / n_want;
-  if (g_ctx.host_chunk > 0) chunk = std::min(g_ctx.host_chunk, n_flights);
-  const int n_chunks = (n_flights + chunk - 1) / chunk;
+  // Chunk schedule: equal chunks of ~4 flights per SM (measured best on the 4096-flight ensemble: smaller chunks
+  // leave CTA slots empty, larger ones expose more of the first H2D and the last D2H).
+  std::vector<int> starts;                      // flight index where chunk c begins; starts.back() = n_flights
+  {
+    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 4 * g_ctx.sm_count;
+    if ((size_t)chunk_cap * n_frames * 152 > ((size_t)3 << 30))           // bound the staging buffers (2 x chunk)
+      chunk_cap = std::max<int>(1, (int)(((size_t)3 << 30) / ((size_t)n_frames * 152)));
+    const int n_want = (n_flights + chunk_cap - 1) / chunk_cap;
+    for (int i = 0; i < n_want; i++) starts.push_back((int)((long long)n_flights * i / n_want));
+    starts.push_back(n_flights);
+  }
+  const int n_chunks = (int)starts.size() - 1;
+  int chunk = 0;                                // largest chunk: size of the staging buffers
+  for (int c = 0; c < n_chunks; c++) chunk = std::max(chunk, starts[c + 1] - starts[c]);
   cudaError_t e = cudaSuccess;
   // everything the caller queued on its stream happens before the pipeline starts
   cudaEvent_t ev_start = P.st[0].out_done;            // any event will do before the first D2H uses it
@@ -105,7 +111,7 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
 
   auto upload = [&](int c) -> cudaError_t {
     Stage& S = P.st[c & 1];
-    const int f0 = c * chunk, nf = std::min(chunk, n_flights - f0);
+    const int f0 = starts[c], nf = starts[c + 1] - f0;
     const size_t o = (size_t)f0 * n_frames, n = (size_t)nf * n_frames;
     cudaError_t r = cudaSuccess;
     if (c >= 2) r = cudaStreamWaitEvent(P.s_in, P.st[c & 1].computed, 0);     // inputs of chunk c-2 consumed
@@ -127,7 +133,7 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   if ((e = upload(0)) != cudaSuccess) return cuda_fail(e, "H2D");
   for (int c = 0; c < n_chunks; c++) {
     Stage& S = P.st[c & 1];
-    const int f0 = c * chunk, nf = std::min(chunk, n_flights - f0);
+    const int f0 = starts[c], nf = starts[c + 1] - f0;
     const size_t o = (size_t)f0 * n_frames, n = (size_t)nf * n_frames;
     if (c + 1 < n_chunks && (e = upload(c + 1)) != cudaSuccess) return cuda_fail(e, "H2D");
     WorkScope scope(c & 1);
