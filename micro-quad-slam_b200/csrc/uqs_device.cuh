@@ -32,6 +32,7 @@ constexpr int      kMaxRayCells   = 1024;       // magic-division exactness boun
 constexpr uint32_t kRayHit        = 1u << 24;
 constexpr uint32_t kRayValid      = 1u << 25;
 constexpr uint32_t kFrameHasOrigin = 1u << 16;
+constexpr uint32_t kFrameSorted    = 1u << 17;   // the frame's beams are in circular angular order (exact test)
 constexpr uint32_t kEmptyBoxLoHi  = 0x00007fffu;  // min = 0x7fff, max = 0  -> never overlaps
 
 // ---------------------------------------------------------------------------

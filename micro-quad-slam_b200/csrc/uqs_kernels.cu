@@ -251,7 +251,8 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
     // radius k, so beams i,j are apart for every k > 1/|sigma_i - sigma_j|.  Conservative
     // float arithmetic (K0 may only be too large) -- it gates a fast path, never a result.
     int k0 = 0;
-    if (want_k0) {                       // only the grid-resident engine reads K0
+    bool frame_sorted = false;
+    if (want_k0) {                       // only the grid-resident engine reads K0 and the order flag
       const int dx = sext12(w0), dy = sext12(w0 >> 12);
       const int adx = abs(dx), ady = abs(dy);
       const bool xmaj = adx >= ady;
@@ -272,15 +273,28 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
       const int nxt = above ? (__ffs(above) - 1) : (__ffs(dir) - 1);
       const float sn = __shfl_sync(0xffffffffu, sigma, nxt & 31);
       const bool has_dir = m >= 1;
-      float gap = sn - sigma;                                           // to the next beam, cyclically
-      const bool wraps = has_dir && gap < 0.f;
-      if (wraps) gap += 8.f;
+      float gap = sn - sigma;                                           // to the next beam, cyclically (K0 only)
+      // exact order test: sigma = A + s*n/m as integers (A in {0,2,4,6,8}); sigma_i <= sigma_next  <=>
+      // (A' - A)*m*m' + s'*n'*m - s*n*m' >= 0.  8 is the same direction as 0.
+      int A = (int)ra, sgn_n = (rb > 0.f) ? n : -n;
+      if (A == 8 && n == 0) A = 0;
+      const int pk = (A << 24) | ((sgn_n & 0xfff) << 12) | (max(m, 0) & 0xfff);     // m <= 1024 < 4096
+      const int pn = __shfl_sync(0xffffffffu, pk, nxt & 31);
+      const int A2 = pn >> 24, n2s = (pn << 8) >> 20, m2 = pn & 0xfff;
+      const int order = (A2 - A) * m * m2 + n2s * m - sgn_n * m2;
+      const bool wraps = has_dir && order < 0;
+      // the float gap only feeds the (conservative) K0: make it agree with the exact order first
+      if (order == 0) gap = 0.f;                     // parallel beams: shared up to the shorter one's end
+      else if (order < 0) gap += 8.f;                // the one passage through 8 -> 0
+      gap = fmaxf(gap, 0.f);
       // circularly sorted <=> the cyclic sequence passes 8 -> 0 at most once
       const bool sorted = __popc(__ballot_sync(0xffffffffu, wraps)) <= 1;
+      frame_sorted = sorted;
       if (__popc(any) >= 2) {
         if (sorted || __popc(dir) < 2) {
           int kk = 1;                                                   // the start cell is shared by all beams
-          if (has_dir && __popc(dir) >= 2) kk = (gap > 1e-4f) ? (int)(1.0f / (gap - 2e-5f)) + 2 : 0x7fffffff;
+          // no shared cell once k*gap > 1: steps 0..floor(1/gap) may collide (the float slack only enlarges it)
+          if (has_dir && __popc(dir) >= 2) kk = (gap > 1e-4f) ? (int)(1.0f / (gap - 2e-5f)) + 1 : 0x7fffffff;
           k0 = min(__reduce_max_sync(0xffffffffu, kk), mmax + 1);
         } else {
           // beams out of angular order (very short rays quantise coarsely): exact all-pairs bound
@@ -291,7 +305,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
             const int mp = __shfl_sync(0xffffffffu, m, pl);
             float dlt = fabsf(sigma - sp);
             dlt = fminf(dlt, 8.f - dlt);
-            int kk = (dlt > 1e-4f) ? (int)(1.0f / (dlt - 2e-5f)) + 2 : 0x7fffffff;
+            int kk = (dlt > 1e-4f) ? (int)(1.0f / (dlt - 2e-5f)) + 1 : 0x7fffffff;
             if (m < 1 || mp < 1) kk = 1;
             kk = min(kk, min(m, mp) + 1);          // a beam has no step beyond its own length
             if (m >= 0 && mp >= 0) k0 = max(k0, kk);
@@ -307,7 +321,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
     ymax = __reduce_max_sync(0xffffffffu, ymax);
     if (lane == 0)
       frames[fi] = make_uint4(have_o ? ((uint32_t)gx0 | ((uint32_t)k0 << 16)) : 0u,
-                              have_o ? ((uint32_t)gy0 | kFrameHasOrigin) : 0u,
+                              have_o ? ((uint32_t)gy0 | kFrameHasOrigin | (frame_sorted ? kFrameSorted : 0u)) : 0u,
                               (uint32_t)xmin | ((uint32_t)xmax << 16),
                               (uint32_t)ymin | ((uint32_t)ymax << 16));
   }
@@ -772,7 +786,7 @@ k_replay_flights(FlightArgs A) {
       sts_v4(at + 16u * (uint32_t)lane, b.inv, (uint32_t)b.n2 | ((uint32_t)(b.m + 1) << 16),
              ((uint32_t)b.sM & 0xffffu) | ((uint32_t)b.sN << 16),
              ((uint32_t)b.end_delta & 0xffu) | ((uint32_t)b.ra << 8) | (b.rb < 0 ? 0x1000u : 0u));
-      if (lane == 0) sts_v4(at + 512u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, 0u);
+      if (lane == 0) sts_v4(at + 512u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, (org.y & kFrameSorted) ? 1u : 0u);
     };
     if (w < L && w < A.n_frames)
       decode_store(__ldg(&rays[(size_t)w * 32 + lane]), __ldg(reinterpret_cast<const uint2*>(&frames[w])), w);
@@ -797,6 +811,7 @@ k_replay_flights(FlightArgs A) {
       B.rb = (dv.w & 0x1000u) ? -1 : 1;
       B.k0 = (int)fv.y;
       const int base = (int)fv.x, mmax = (int)fv.z;
+      const bool sorted = fv.w != 0u;
       const int kshared = min(B.k0, mmax + 1);
 
       // ---- steps k < K0: beams may meet in a cell; detect and keep beam order --------------------
@@ -805,6 +820,35 @@ k_replay_flights(FlightArgs A) {
         const int q = minor_steps(k, n2, h2, inv);
         const int addr = base + k * sM + q * sN;
         const int delta = (k == m) ? B.end_delta : -lo_free;
+        const unsigned actm0 = __ballot_sync(0xffffffffu, act);
+        if (sorted && !__any_sync(0xffffffffu, act && k == m)) {
+          // Beams in angular order and only free-space steps here: the beams on one cell are a run of
+          // consecutive ACTIVE lanes (possibly wrapping from the last to the first), and the -free
+          // steps commute, so the head of each run applies the run length at once.
+          if (actm0 == 0u) continue;
+          const unsigned lower = actm0 & ((1u << lane) - 1u);
+          const int prev = lower ? (31 - __clz(lower)) : lane;
+          const int paddr = __shfl_sync(0xffffffffu, addr, prev);
+          const bool headr = act && (lower == 0u || paddr != addr);
+          const unsigned heads = __ballot_sync(0xffffffffu, headr);
+          const int first = __ffs(actm0) - 1, last = 31 - __clz(actm0);
+          const int a_first = __shfl_sync(0xffffffffu, addr, first), a_last = __shfl_sync(0xffffffffu, addr, last);
+          const unsigned above_h = heads & ~(0xffffffffu >> (31 - lane));           // heads above this lane
+          const unsigned span = above_h ? ((1u << (__ffs(above_h) - 1)) - 1u) : 0xffffffffu;
+          int len = __popc(actm0 & span & ~((1u << lane) - 1u));                     // active lanes of my run
+          bool apply = headr;
+          if ((heads & (heads - 1u)) != 0u && a_first == a_last) {                   // first run continues the last
+            const int len_first = __shfl_sync(0xffffffffu, len, first);
+            if (lane == 31 - __clz(heads)) len += len_first;
+            if (lane == first) apply = false;
+          }
+          if (apply) {
+            const uint32_t cell = grid_sa + (uint32_t)addr;
+            sts_u8(cell, max(lds_s8(cell) - len * lo_free, lo_min));
+          }
+          __syncwarp();
+          continue;
+        }
         // runs of consecutive lanes on one cell (beams are ordered by angle, so nearly all
         // collisions are between neighbours); only the head of a run enters the ring table
         const unsigned key = act ? (unsigned)addr : (0x80000000u | (unsigned)lane);
@@ -858,19 +902,20 @@ k_replay_flights(FlightArgs A) {
       int k = w + ((max(B.k0 - w, 0) + NW - 1) / NW) * NW;
       const uint32_t gbase = grid_sa + (uint32_t)base;
       const int free_delta = -lo_free;
-      for (; k <= mmax; k += 4 * NW) {
-        uint32_t addr[4];
-        int val[4];
+      constexpr int UN = 4;                         // steps in flight per warp (8 was measured slower)
+      for (; k <= mmax; k += UN * NW) {
+        uint32_t addr[UN];
+        int val[UN];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < UN; u++) {
           const int ku = k + u * NW;
           const uint32_t a = gbase + (uint32_t)(ku * sM + minor_steps(ku, n2, h2, inv) * sN);
           addr[u] = (ku <= m) ? a : dummy_sa;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) val[u] = lds_s8(addr[u]);
+        for (int u = 0; u < UN; u++) val[u] = lds_s8(addr[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < UN; u++) {
           const int v = val[u] + ((k + u * NW == m) ? B.end_delta : free_delta);
           sts_u8(addr[u], min(max(v, lo_min), lo_max));
         }
