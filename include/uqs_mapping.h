@@ -107,14 +107,16 @@ int  uqs_profile_collect(double ms[3], int counts[3]);
 /* Block until everything enqueued so far has finished. */
 int  uqs_sync(void);
 
-/* Kernel tuning knobs (0 keeps the built-in choice).  sub-tile = the square of
+/* Kernel tuning knobs (0 keeps the built-in choice).  sub-tile = the rectangle of
  * cells one warp owns in shared memory; time_slices > 1 splits a flight's frames
- * into contiguous slices that are replayed concurrently and composed exactly. */
+ * into contiguous slices that are replayed concurrently and composed exactly
+ * (1 = never slice).  Any setting produces identical bytes. */
 int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
 /* Replay engine: 0 = automatic (grid resident in one CTA's shared memory when W*H fits
  * 227 KB, warp-owned sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
- * (error if it does not fit).  flight_warps = warps per CTA of the resident engine
- * (0, 8, 16 or 32).  Both engines produce identical bytes. */
+ * (error if the flights' touched bounding box does not fit).  flight_warps = warps
+ * per CTA of the resident engine (0 = automatic, 4, 8, 16 or 32).  Both engines
+ * produce identical bytes. */
 int  uqs_set_engine(int engine, int flight_warps);
 
 /*

@@ -716,13 +716,6 @@ __device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int bx0
   return b;
 }
 
-// one saturating update of a resident cell
-__device__ __forceinline__ void rmw_cell(int8_t* cell, int delta, int lo_min, int lo_max) {
-  int v = (int)*cell + delta;
-  v = min(max(v, lo_min), lo_max);
-  *cell = (int8_t)v;
-}
-
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 8 : ((NW <= 8) ? 4 : ((NW <= 16) ? 2 : 1)))
 k_replay_flights(FlightArgs A) {
