@@ -112,8 +112,9 @@ int  uqs_sync(void);
  * into contiguous slices that are replayed concurrently and composed exactly
  * (1 = never slice).  Any setting produces identical bytes. */
 int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
-/* Replay engine: 0 = automatic (grid resident in one CTA's shared memory when W*H fits
- * 227 KB, warp-owned sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
+/* Replay engine: 0 = automatic (each flight's touched bounding box resident in one CTA's
+ * shared memory when several such CTAs fit an SM and there is at least one flight per
+ * SM; warp-owned sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
  * (error if the flights' touched bounding box does not fit).  flight_warps = warps
  * per CTA of the resident engine (0 = automatic, 4, 8, 16 or 32).  Both engines
  * produce identical bytes. */
