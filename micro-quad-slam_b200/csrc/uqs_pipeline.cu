@@ -73,15 +73,23 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   if (rc) return rc;
   const bool flow = L.t_ms != nullptr;
   const size_t cells = (size_t)p->W * p->H;
-  // Chunk schedule: equal chunks of ~4 flights per SM (measured best on the 4096-flight ensemble: smaller chunks
-  // leave CTA slots empty, larger ones expose more of the first H2D and the last D2H).
+  // Chunk schedule: chunks of ~5 flights per SM after a short ramp (measured on the 4096-flight ensemble: smaller
+  // chunks leave CTA slots empty, larger ones expose more of the first H2D and the last D2H).
   std::vector<int> starts;                      // flight index where chunk c begins; starts.back() = n_flights
   {
-    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 4 * g_ctx.sm_count;
+    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 5 * g_ctx.sm_count;
     if ((size_t)chunk_cap * n_frames * 152 > ((size_t)3 << 30))           // bound the staging buffers (2 x chunk)
       chunk_cap = std::max<int>(1, (int)(((size_t)3 << 30) / ((size_t)n_frames * 152)));
-    const int n_want = (n_flights + chunk_cap - 1) / chunk_cap;
-    for (int i = 0; i < n_want; i++) starts.push_back((int)((long long)n_flights * i / n_want));
+    if (g_ctx.host_chunk == 0 && n_flights >= 3 * chunk_cap) {
+      // ramp: 1 then 2 flights per SM first (their H2D cannot hide behind any kernel), then full chunks
+      int f = 0;
+      for (int c : { g_ctx.sm_count, 2 * g_ctx.sm_count }) { starts.push_back(f); f += c; }
+      const int body = n_flights - f, n_mid = (body + chunk_cap - 1) / chunk_cap;
+      for (int i = 0; i < n_mid; i++) starts.push_back(f + (int)((long long)body * i / n_mid));
+    } else {
+      const int n_want = (n_flights + chunk_cap - 1) / chunk_cap;
+      for (int i = 0; i < n_want; i++) starts.push_back((int)((long long)n_flights * i / n_want));
+    }
     starts.push_back(n_flights);
   }
   const int n_chunks = (int)starts.size() - 1;
@@ -203,7 +211,7 @@ int uqs_replay_flow(const uqs_params* p, int n_flights, int n_samples, const uin
 
 /* Flights per chunk of the host-buffer pipeline (0 = automatic). */
 int uqs_set_host_chunk(int flights) {
-  if (flights < 0) { set_error("negative chunk"); return UQS_ERR_BAD_ARG; }
+  if (flights < -1) { set_error("negative chunk"); return UQS_ERR_BAD_ARG; }
   g_ctx.host_chunk = flights;
   return UQS_OK;
 }

@@ -25,7 +25,7 @@ for _ in range(2):
 print(f"D2H grids {g.numel()/1e9:.2f} GB in {dt*1e3:.1f} ms = {g.numel()/dt/1e9:.1f} GB/s")
 for stream_mode in ("torch",):
     m.set_stream(None if stream_mode == "own" else torch.cuda.current_stream().cuda_stream)
-    for chunk in (148, 222, 296, 384, 512, 683, 0):
+    for chunk in (740, 888, 0, 0):
         m.set_host_chunk(chunk)
         for rep in range(2):
             t0 = time.perf_counter()
