@@ -197,7 +197,7 @@ def recorded_traffic(w):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference_arm(args, synth):
+def run_reference_arm(args, synth, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -225,7 +225,7 @@ def run_reference_arm(args, synth):
     wall = sum(times) / len(times)
     value = U / wall
     sample = f"{n} of {w.n_flights} flights per step ({fpc} per worker process), P0 + mapping, logs in RAM"
-    print(json.dumps({
+    out_fd.emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i8", "data": "synthetic", "config": describe(w, args.gpus), "frames_per_s": n * w.n_frames / wall,
@@ -234,7 +234,22 @@ def run_reference_arm(args, synth):
     }))
 
 
+class OneLineStdout:
+    """Everything any library prints to fd 1 (NCCL's version banner, ...) goes to stderr; only emit() writes to the
+    real stdout -- the driver reads ONE JSON line from it."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main():
+    out_fd = OneLineStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -253,7 +268,7 @@ def main():
     m = importlib.import_module("micro-quad-slam_b200")
     synth = importlib.import_module("micro-quad-slam_b200.synth")
     if args.impl == "reference":
-        run_reference_arm(args, synth)
+        run_reference_arm(args, synth, out_fd)
         return
 
     import torch
@@ -269,7 +284,6 @@ def main():
     dev = torch.device("cuda", local)
     local_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("UQS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     m.init(local)                                   # fails loudly if the CUDA library cannot run
     m.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -405,7 +419,7 @@ def main():
            "data": "synthetic", "config": describe(w, world), "frames_per_s": F * NF * world / (ms_per_step * 1e-3),
            "ray_cell_updates_per_step": total_updates, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
            "gpu_launches": int(launches), "clocks": clk, "host": {"cpus": os.cpu_count(), "rank_local_cpus": local_cpus}}
-    print(json.dumps(out))
+    out_fd.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
