@@ -659,7 +659,7 @@ int uqs_measure_rmw_peak(double* updates_per_s) {
   if (rc) return rc;
   if (!updates_per_s) { set_error("NULL output"); return UQS_ERR_BAD_ARG; }
   cudaStream_t st = g_ctx.stream();
-  const int tile_bytes = 6400, iters = 4096;
+  const int tile_bytes = 4096, iters = 8192;
   const size_t smem = (size_t)tile_bytes * kReplayWarps;
   cudaError_t e = cudaFuncSetAttribute(k_rmw_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_rmw_peak)");

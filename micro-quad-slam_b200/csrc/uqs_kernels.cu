@@ -994,21 +994,23 @@ cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, 
 // ===========================================================================
 __global__ void __launch_bounds__(kReplayThreads)
 k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink) {
+  // Ceiling of the update itself: every warp read-modify-writes bytes of its own shared-memory tile, 32 consecutive
+  // bytes per warp instruction (8 banks, one wavefront, no conflict), eight independent updates in flight, and
+  // nothing else -- no ray arithmetic, no clipping, no collisions.  tile_bytes must be a power of two >= 2048.
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   int8_t* tile = reinterpret_cast<int8_t*>(uqs_smem) + (size_t)wic * tile_bytes;
   for (int i = lane; i < tile_bytes; i += 32) tile[i] = 0;
   __syncwarp();
-  const int span = tile_bytes / 32;          // each lane walks its own 4-byte-aligned words
-  int off = 0;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)lane;
+  const uint32_t mask = (uint32_t)tile_bytes - 1u;
+  uint32_t off = 0;
   for (int it = 0; it < iters; it++) {
-#pragma unroll 8
-    for (int u = 0; u < 8; u++) {
-      int8_t* cell = tile + ((off + u * 37) % span) * 32 + lane;   // 32 consecutive bytes: 8 banks, no conflict
-      int v = (int)*cell - 1;
-      v = max(v, lo_min);
-      *cell = (int8_t)v;
-    }
-    off += 8 * 37;
+    int v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = lds_s8(base + ((off + 32u * u) & mask));
+#pragma unroll
+    for (int u = 0; u < 8; u++) sts_u8(base + ((off + 32u * u) & mask), max(v[u] - 1, lo_min));
+    off += 256u + 32u;
   }
   __syncwarp();
   if (tile[lane] == 77) *sink = 1;
