@@ -455,3 +455,55 @@ def test_dropin_symbols_replay_like_log_tick(gpu, oracle, orc_mod, synth):
             if i % 97 == 0:
                 ref.raycast_update(float(d["x_true"][0, i]), float(d["y_true"][0, i]), float(d["x_true"][0, i]) + 1.5, float(d["y_true"][0, i]) - 0.7, True)
         assert np.array_equal(got, ref.grid())
+
+
+# ----------------------------------------------------------------------------------------------
+# randomized stress: odd geometries and sensor constants against the oracle, every engine
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(40))
+def test_random_geometry_and_sensor_constants(gpu, oracle, seed):
+    """fov from 2 deg (beams almost parallel: collisions far out, large K0) to 170 deg (fans overlap: beams NOT in
+    angular order, the all-pairs K0 / table path), coarse and fine cells, widths not divisible by 4, moved origins,
+    short and long ranges, hovering and jumping poses -- sub-tile, time-sliced and resident engines must all equal
+    the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    W = int(rng.choice([62, 90, 101, 128, 250, 333, 400]))
+    H = int(rng.choice([58, 96, 127, 200, 260, 400]))
+    res = float(rng.choice([0.02, 0.05, 0.1, 0.25]))
+    p = gpu.make_params(W, H, res, W * res)
+    p.fov_deg = np.float32(rng.choice([2.0, 10.0, 63.0, 90.0, 120.0, 170.0]))
+    p.max_range_m = np.float32(rng.choice([1.0, 4.0, 6.0]))
+    p.origin_x, p.origin_y = np.float32(rng.uniform(-1, 1)), np.float32(rng.uniform(-1, 1))
+    p.lo_free, p.lo_occ = int(rng.choice([1, 2, 5])), int(rng.choice([3, 6, 20]))
+    p.lo_min, p.lo_max = int(rng.choice([-80, -128, -5])), int(rng.choice([80, 127, 7]))
+    F, N = int(rng.choice([1, 2, 5])), int(rng.choice([40, 333, 700]))
+    half_x, half_y = 0.5 * W * res, 0.5 * H * res
+    mode = rng.integers(3)
+    if mode == 0:      # hover
+        x = (p.origin_x + 0.01 * rng.standard_normal((F, N))).astype(np.float32)
+        y = (p.origin_y + 0.01 * rng.standard_normal((F, N))).astype(np.float32)
+    elif mode == 1:    # jumps all over (and beyond) the map
+        x = rng.uniform(-1.2 * half_x, 1.2 * half_x, (F, N)).astype(np.float32)
+        y = rng.uniform(-1.2 * half_y, 1.2 * half_y, (F, N)).astype(np.float32)
+    else:              # smooth drift
+        t = np.linspace(0, 1, N, dtype=np.float32)
+        x = (np.float32(0.7 * half_x) * np.cos(6 * t) + np.zeros((F, 1), np.float32)).astype(np.float32)
+        y = (np.float32(0.7 * half_y) * np.sin(4 * t) + np.zeros((F, 1), np.float32)).astype(np.float32)
+    yaw = rng.uniform(-360, 360, (F, N)).astype(np.float32)
+    r = rng.uniform(0.0, float(p.max_range_m) * 1.1, (F, N, 32)).astype(np.float32)
+    r[rng.random(r.shape) < 0.1] = np.nan
+    r[rng.random(r.shape) < 0.1] = np.float32(rng.uniform(0.04, 3 * res))       # very short rays
+    want, U = oracle.replay_flights(p, x, y, yaw, r)
+    cases = [(1, 0, 1), (1, 0, 3), (0, 0, 0)]
+    if max(W, H) <= 400:
+        cases += [(2, 4, 0), (2, 16, 0)]
+    try:
+        for engine, nw, slices in cases:
+            gpu.set_engine(engine, nw)
+            gpu.set_tuning(0, 0, slices)
+            got, st = gpu.replay(p, x, y, yaw, r)
+            assert np.array_equal(got, want), ((engine, nw, slices), dict(W=W, H=H, res=res, fov=float(p.fov_deg)), first_diff(got, want))
+            assert st["ray_cell_updates"] == U
+    finally:
+        gpu.set_engine(0, 0)
+        gpu.set_tuning(0, 0, 0)
