@@ -105,6 +105,19 @@ int make_dev_params(const uqs_params* p, DevParams* d) {
   return UQS_OK;
 }
 
+// magic reciprocals of the closed-form Bresenham, built once per device (uqs_device.cuh: minor_steps)
+int ensure_inv_table() {
+  if (g_ctx.inv_table.p) return UQS_OK;
+  std::vector<uint32_t> t(kMaxRayCells + 1);
+  t[0] = 0;
+  for (uint32_t m = 1; m <= (uint32_t)kMaxRayCells; m++) t[m] = (uint32_t)(((1ull << 31) + m - 1) / m);
+  int rc = g_ctx.inv_table.ensure(t.size() * sizeof(uint32_t));
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpy(g_ctx.inv_table.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { g_ctx.inv_table.release(); return cuda_fail(e, "inv table upload"); }
+  return UQS_OK;
+}
+
 // sub-tile geometry for a grid of W columns and `rows` owned rows, aiming at `target`-cell sub-tiles
 static void choose_tiles(int W, int rows, int target, int* sw, int* sh, int* nsx, int* nsy) {
   auto pick = [](int extent, int forced, int target, int* size, int* count) {
@@ -129,6 +142,10 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
                   int accumulate, int row0, int rows, bool reset_stats) {
   cudaStream_t st = g_ctx.stream();
   const int gpf = (n_frames + 31) / 32;
+  {
+    const int rc0 = ensure_inv_table();
+    if (rc0) return rc0;
+  }
   // Sub-tile engine geometry.  With plenty of (flight, tile) jobs, ~80-cell tiles and no time slicing.
   // With few (one long log, one small flight) the chip would idle: cut the log into S time slices,
   // replayed concurrently as clamp-add maps on 40-cell tiles and composed afterwards (exact).
@@ -210,7 +227,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     KernelTimer t_setup(1);
     k_ray_setup<<<(unsigned)(nf * gpf), 1024, 0, st>>>(
         dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, may_reside ? 1 : 0,
-        (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
+        (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
     e = cudaGetLastError();
     t_setup.stop();
     if (e != cudaSuccess) return cuda_fail(e, "k_ray_setup launch");
@@ -607,6 +624,7 @@ int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const floa
   DevParams dp;
   if ((rc = make_dev_params(p, &dp))) return rc;
   if (n_frames <= 0 || !x || !y || !yaw || !ranges || !cells_out || !origin_out) { set_error("uqs_beam_cells: bad argument"); return UQS_ERR_BAD_ARG; }
+  if ((rc = ensure_inv_table())) return rc;
   cudaStream_t st = g_ctx.stream();
   const size_t n = (size_t)n_frames;
   const int gpf = (n_frames + 31) / 32;
@@ -621,7 +639,7 @@ int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const floa
   if (e != cudaSuccess) return cuda_fail(e, "memset");
   k_ray_setup<<<(unsigned)gpf, 1024, 0, st>>>(dp, n_frames, gpf, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p,
                                               (float*)g_ctx.in_yaw.p, (float*)g_ctx.in_ranges.p, nullptr, 0,
-                                              (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p,
+                                              (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p,
                                               (uint2*)g_ctx.w->rays.p, (unsigned long long*)g_ctx.w->counters.p);
   int32_t* d_cells = (int32_t*)g_ctx.out_grids.p;
   int32_t* d_origin = d_cells + n * 64;

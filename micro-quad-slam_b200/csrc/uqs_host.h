@@ -44,6 +44,7 @@ struct Context {
   int host_chunk = 0;                           // flights per chunk of the host-buffer pipeline (0 = auto)
   size_t scratch_budget = (size_t)12 << 30;     // ray/frame records held at once
   unsigned long long launches = 0;              // kernels launched by this library
+  DevBuf inv_table;                             // ceil(2^31 / m) for m = 0..kMaxRayCells (0 at m = 0)
   // scratch: works[0] serves the device-pointer API and the drop-in, works[1..2] the pipeline
   Work works[3];
   Work* w = &works[0];
@@ -61,6 +62,7 @@ struct Context {
     DevBuf* all[] = { &in_t, &in_rx, &in_ry, &in_h, &in_yaw, &in_q, &in_x, &in_y, &in_ranges, &in_kind, &out_grids };
     for (DevBuf* b : all) b->release();
     for (Work& k : works) k.release();
+    inv_table.release();
   }
 };
 
@@ -76,6 +78,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
                   const float* yaw, const float* ranges, const uint8_t* kind, int8_t* grids,
                   int accumulate, int row0, int rows, bool reset_stats);
 int fetch_stats(uqs_stats* stats, uint64_t frames);
+int ensure_inv_table();
 int fetch_stats_mask(uqs_stats* stats, uint64_t frames, unsigned mask);
 void dropin_release();
 void pipeline_release();

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(1024, 2)
 k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __restrict__ x,
             const float* __restrict__ y, const float* __restrict__ yaw_deg,
             const float* __restrict__ ranges, const uint8_t* __restrict__ kind, int want_k0,
-            uint4* __restrict__ frames, uint2* __restrict__ groups, uint2* __restrict__ rays,
+            const uint32_t* __restrict__ inv_table, uint4* __restrict__ frames, uint2* __restrict__ groups, uint2* __restrict__ rays,
             unsigned long long* __restrict__ stats /* [4]: U, accepted, skipped, domain */) {
   __shared__ int s_box[4][32];
   __shared__ unsigned long long s_cnt[4][32];
@@ -204,12 +204,23 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
   unsigned long long cells = 0;
   int accepted = 0, skipped = 0, domain = 0;
 
+  // the start cell is per frame, not per beam: warp 0 computes it for the block's 32 frames (lane = frame)
+  __shared__ int s_org[32][2];
+  if (w == 0) {
+    int ox = -1, oy = -1;
+    const int fo = g * 32 + lane;
+    if (fo < n_frames && !world_to_grid(p, x[fbase + fo], y[fbase + fo], ox, oy)) ox = oy = -1;
+    s_org[lane][0] = ox;
+    s_org[lane][1] = oy;
+  }
+  __syncthreads();
+
   if (f < n_frames) {
     const size_t fi = fbase + f;
     const float px = x[fi], py = y[fi], third = yaw_deg[fi];
     const bool raw = kind != nullptr && kind[fi] == 1;
-    int gx0, gy0;
-    const bool have_o = world_to_grid(p, px, py, gx0, gy0);
+    const int gx0 = s_org[w][0], gy0 = s_org[w][1];
+    const bool have_o = gx0 >= 0;
     float ex = 0.f, ey = 0.f;
     bool hit = false;
     int st;
@@ -234,7 +245,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
         } else {
           w0 = ((uint32_t)dx & 0xfffu) | (((uint32_t)dy & 0xfffu) << 12) | (hit ? kRayHit : 0u) |
                kRayValid;
-          w1 = m ? (0x7fffffffu / (unsigned)m + 1u) : 0u;      // ceil(2^31 / m) in 32-bit arithmetic
+          w1 = __ldg(&inv_table[m]);                           // ceil(2^31 / m), 0 for m == 0
           xmin = min(gx0, gx1); xmax = max(gx0, gx1);
           ymin = min(gy0, gy1); ymax = max(gy0, gy1);
           cells = (unsigned long long)m + 1;

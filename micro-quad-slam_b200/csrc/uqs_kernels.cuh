@@ -62,7 +62,8 @@ int pose_scan_threads();
 
 __global__ void k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* x,
                             const float* y, const float* yaw_deg, const float* ranges,
-                            const uint8_t* kind, int want_k0, uint4* frames, uint2* groups, uint2* rays,
+                            const uint8_t* kind, int want_k0, const uint32_t* inv_table, uint4* frames, uint2* groups,
+                            uint2* rays,
                             unsigned long long* stats);
 __global__ void k_records_to_cells(long long n_frames, const uint4* frames, const uint2* rays,
                                    int32_t* cells, int32_t* origin);
