@@ -155,12 +155,23 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     const long long warp_slots = (long long)g_ctx.sm_count * 32;
     const long long jobs80 = (long long)n_flights * nsx * nsy;
     int want = g_ctx.tune_slices;
+    int slice_tile = 40;
     if (want == 0 && jobs80 < 2 * warp_slots) {
-      int sw4, sh4, nx4, ny4;
-      choose_tiles(dp.W, rows, 40, &sw4, &sh4, &nx4, &ny4);
-      const long long jobs40 = (long long)n_flights * nx4 * ny4;
-      want = (int)std::min<long long>(64, std::max<long long>(1, 16 * warp_slots / std::max<long long>(jobs40, 1)));
-      want = std::min(want, std::max(1, gpf / 8));                  // at least 256 frames per slice
+      // largest map tile that still yields >= 8 jobs per warp slot at the finest admissible slicing (>= 256
+      // frames per slice, <= 64 slices).  Measured: 56-cell tiles win for long rays (>= 200 cells: the one-hour
+      // log at 1 cm), 40 for short ones (two more CTAs per SM matter more), smaller only when jobs are scarce.
+      const int s_max = std::max(1, std::min(64, gpf / 8));
+      const bool long_rays = dp.max_range >= 200.0f * dp.res;
+      long long jobs_t = 1;
+      for (int t : { 56, 40, 24, 16 }) {
+        if (t == 56 && !long_rays) continue;
+        int a, b, nx, ny;
+        choose_tiles(dp.W, rows, t, &a, &b, &nx, &ny);
+        slice_tile = t;
+        jobs_t = (long long)n_flights * nx * ny;
+        if (jobs_t * s_max >= 8 * warp_slots) break;
+      }
+      want = (int)std::min<long long>(s_max, std::max<long long>(1, (16 * warp_slots + jobs_t - 1) / jobs_t));
     }
     if (want > 1) {
       const size_t map_bytes = (size_t)dp.W * dp.H * 4;
@@ -169,7 +180,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     }
     if (want > 1) {
       slices = want;
-      choose_tiles(dp.W, rows, 40, &sw, &sh, &nsx, &nsy);
+      choose_tiles(dp.W, rows, slice_tile, &sw, &sh, &nsx, &nsy);
     }
   }
   int pitch = (sw + 3) & ~3;
