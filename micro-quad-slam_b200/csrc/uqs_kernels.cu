@@ -445,6 +445,7 @@ __device__ __forceinline__ int in_reg(int v) {
   return v;
 }
 
+
 struct TileConsts { int pitch, lo_free, lo_occ, lo_min, lo_max, end_nohit; };
 
 // floor(num / den) for 0 <= num < 2^22, 1 <= den <= 1024: one reciprocal multiply and a +-1 fix-up
@@ -481,6 +482,11 @@ __device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, 
   bool live;
   {
     const int dx = sext12(rec.x), dy = sext12(rec.x >> 12);
+    // cheap reject first: a frame's box covers the whole fan, most sub-tiles inside it see no beam at all
+    const int ex = gx0 + dx, ey = gy0 + dy;
+    const bool near = (rec.x & kRayValid) != 0u && min(gx0, ex) < X1 && max(gx0, ex) >= X0 && min(gy0, ey) < Y1 &&
+                      max(gy0, ey) >= Y0;
+    if (!__any_sync(0xffffffffu, near)) return;
     const int adx = abs(dx), ady = abs(dy);
     const bool xmaj = adx >= ady;
     const int m = xmaj ? adx : ady, n = xmaj ? ady : adx, h = m >> 1;
@@ -739,9 +745,13 @@ k_replay_flights(FlightArgs A) {
   uint8_t* ring = reinterpret_cast<uint8_t*>(uqs_smem) + (size_t)P * A.max_rows + (size_t)w * A.ring_size;
   const int ring_mask = A.ring_size - 1;
   const uint32_t grid_sa = (uint32_t)__cvta_generic_to_shared(grid_s);
-  // scratch byte per warp for lanes that have nothing to update (after the collision tables)
-  const uint32_t dummy_sa = grid_sa + (uint32_t)(P * A.max_rows + NW * A.ring_size + 4 * w);
-  const int lo_free = A.lo_free, lo_min = A.lo_min, lo_max = A.lo_max;
+  // The constants of the step loop come back from shared memory through an opaque load: straight from the
+  // parameter bank, ptxas rematerialises them as predicated LDCs inside the unrolled loop (two per step).
+  __shared__ int s_const[2];
+  if (threadIdx.x == 0) { s_const[0] = A.lo_free; s_const[1] = A.lo_min; }
+  __syncthreads();
+  const uint32_t const_sa = (uint32_t)__cvta_generic_to_shared(s_const);
+  const int lo_free = (int)lds_u32(const_sa), lo_min = (int)lds_u32(const_sa + 4u), lo_max = in_reg(A.lo_max);
   const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
   // ring of decoded frames (16-byte aligned, after the scratch words)
   const uint32_t dec_sa = (grid_sa + (uint32_t)(P * A.max_rows + NW * A.ring_size + 4 * NW) + 15u) & ~15u;
@@ -907,21 +917,32 @@ k_replay_flights(FlightArgs A) {
       const uint32_t gbase = grid_sa + (uint32_t)base;
       const int free_delta = -lo_free;
       constexpr int UN = 4;                         // steps in flight per warp (8 was measured slower)
-      for (; k <= mmax; k += UN * NW) {
+      // free-space steps K0 <= k < m only: clamp(v - free) = max(v - free, lo_min) because lo_free >= 0 (one
+      // VIADDMNMX); the end cells of these beams are one extra step of one warp below
+      int mu[UN];                                   // k + u*NW < m  <=>  k < mu[u]
+#pragma unroll
+      for (int u = 0; u < UN; u++) mu[u] = in_reg(m - u * NW);
+      for (; k < mmax; k += UN * NW) {
         uint32_t addr[UN];
         int val[UN];
+        bool on[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) {
           const int ku = k + u * NW;
-          const uint32_t a = gbase + (uint32_t)(ku * sM + minor_steps(ku, n2, h2, inv) * sN);
-          addr[u] = (ku <= m) ? a : dummy_sa;
+          addr[u] = gbase + (uint32_t)(ku * sM + minor_steps(ku, n2, h2, inv) * sN);
+          on[u] = k < mu[u];
         }
 #pragma unroll
-        for (int u = 0; u < UN; u++) val[u] = lds_s8(addr[u]);
+        for (int u = 0; u < UN; u++) if (on[u]) val[u] = lds_s8(addr[u]);
 #pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const int v = val[u] + ((k + u * NW == m) ? B.end_delta : free_delta);
-          sts_u8(addr[u], min(max(v, lo_min), lo_max));
+        for (int u = 0; u < UN; u++) if (on[u]) sts_u8(addr[u], __viaddmax_s32(val[u], free_delta, lo_min));
+      }
+      // end cells of the beams that end at a step >= K0 (q(m) = n): distinct cells, touched by nothing else
+      // in this frame, so any warp may apply them at any time before the frame's barrier
+      if (w == ((f + 1) & (NW - 1)) && mmax >= kshared) {
+        if (m >= kshared) {
+          const uint32_t cell = gbase + (uint32_t)(m * sM + (n2 >> 1) * sN);
+          sts_u8(cell, min(max(lds_s8(cell) + B.end_delta, lo_min), lo_max));
         }
       }
       if ((f & (NW - 1)) == w) {                    // this warp's turn: decode frame f + L, prefetch its next turn
