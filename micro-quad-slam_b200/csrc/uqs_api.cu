@@ -213,6 +213,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   const size_t per_flight = (size_t)n_frames * (32 * sizeof(uint2) + sizeof(uint4)) + (size_t)gpf * sizeof(uint2);
   const size_t budget = g_ctx.scratch_budget;
   int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_flights, budget / std::max<size_t>(per_flight, 1)));
+  chunk = std::min(chunk, 65535);                       // flights are gridDim.y of the ray set-up
   int rc;
   if ((rc = g_ctx.w->rays.ensure((size_t)chunk * n_frames * 32 * sizeof(uint2)))) return rc;
   if ((rc = g_ctx.w->frames.ensure((size_t)chunk * n_frames * sizeof(uint4)))) return rc;
@@ -236,8 +237,8 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     const int nf = std::min(chunk, n_flights - f0);
     const size_t fo = (size_t)f0 * n_frames;
     KernelTimer t_setup(1);
-    k_ray_setup<<<(unsigned)(nf * gpf), 1024, 0, st>>>(
-        dp, n_frames, gpf, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, may_reside ? 1 : 0,
+    k_ray_setup<<<dim3((unsigned)gpf, (unsigned)nf), 1024, 0, st>>>(
+        dp, n_frames, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, may_reside ? 1 : 0,
         (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
     e = cudaGetLastError();
     t_setup.stop();
@@ -648,7 +649,7 @@ int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const floa
     return rc;
   cudaError_t e = cudaMemsetAsync(g_ctx.w->counters.p, 0, 64, st);
   if (e != cudaSuccess) return cuda_fail(e, "memset");
-  k_ray_setup<<<(unsigned)gpf, 1024, 0, st>>>(dp, n_frames, gpf, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p,
+  k_ray_setup<<<(unsigned)gpf, 1024, 0, st>>>(dp, n_frames, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p,
                                               (float*)g_ctx.in_yaw.p, (float*)g_ctx.in_ranges.p, nullptr, 0,
                                               (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p,
                                               (uint2*)g_ctx.w->rays.p, (unsigned long long*)g_ctx.w->counters.p);

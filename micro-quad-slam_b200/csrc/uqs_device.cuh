@@ -42,24 +42,18 @@ constexpr uint32_t kEmptyBoxLoHi  = 0x00007fffu;  // min = 0x7fff, max = 0  -> n
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool sincosf_glibc(float y, float& sn, float& cs) {
   const uint32_t top12 = (__float_as_uint(y) >> 20) & 0x7ffu;
-  double x = (double)y;
-  double xs = x;
-  int n = 0;
-  if (top12 < 0x3f4u) {                       // |y| < pi/4
-    if (top12 < 0x398u) {                     // |y| < 2^-12
-      sn = y;
-      cs = 1.0f;
-      return true;
-    }
-  } else if (top12 < 0x42fu) {                // |y| < 120
-    const double r = __dmul_rn(x, 0x1.45f306dc9c883p+23);
-    n = (__double2int_rz(r) + 0x800000) >> 24;
-    x = __fma_rn(-(double)n, 0x1.921fb54442d18p+0, x);
-    xs = ((n + 1) & 2) ? -x : x;              // sign table {+,-,-,+}[n & 3]
-  } else {
+  if (top12 >= 0x42fu) {                      // |y| >= 120, Inf, NaN
     sn = cs = __int_as_float(0x7fc00000);
     return false;
   }
+  // glibc skips the reduction when |y| < 0.75 (top12 < 0x3f4); running it there gives n = 0 and leaves x
+  // unchanged bit for bit (|y * 2/pi| < 0.48 rounds to 0, fma(-0.0, pi/2, x) == x), so one straight-line
+  // path serves both cases and a warp never executes the polynomial twice.
+  double x = (double)y;
+  const double r = __dmul_rn(x, 0x1.45f306dc9c883p+23);
+  const int n = (__double2int_rz(r) + 0x800000) >> 24;
+  x = __fma_rn(-(double)n, 0x1.921fb54442d18p+0, x);
+  const double xs = ((n + 1) & 2) ? -x : x;   // sign table {+,-,-,+}[n & 3]
   const double x2 = __dmul_rn(x, x);
   const double x3 = __dmul_rn(x2, xs);
   const double x4 = __dmul_rn(x2, x2);
@@ -74,7 +68,9 @@ __device__ __forceinline__ bool sincosf_glibc(float y, float& sn, float& cs) {
   C = __fma_rn(x6, c2, C);
   if (n & 2) C = -C;                          // second table = cosine coefficients negated
   const float fs = __double2float_rn(S), fc = __double2float_rn(C);
+  const bool tiny = top12 < 0x398u;           // |y| < 2^-12: glibc returns (y, 1.0f) before any arithmetic
   if (n & 1) { cs = fs; sn = fc; } else { sn = fs; cs = fc; }
+  if (tiny) { sn = y; cs = 1.0f; }
   return true;
 }
 
@@ -108,7 +104,8 @@ __device__ __forceinline__ int beam_endpoint(const DevParams& p, float px, float
   hit = dist < p.hit_below;
   if (dist > p.max_range) dist = p.max_range;
   const int d = b >> 3, c = b & 7;
-  const float centre = (d == 0) ? 0.0f : (d == 1) ? 90.0f : (d == 2) ? 180.0f : -90.0f;
+  // {0, 90, 180, -90}[d] without a branch (uav_local_nav.c:283)
+  const float centre = (d & 1) ? ((d & 2) ? -90.0f : 90.0f) : ((d & 2) ? 180.0f : 0.0f);
   const float off = p.col_off[c];
   const float ang_deg = __fadd_rn(__fadd_rn(yaw_deg, centre), off);
   const float ang = __fmul_rn(ang_deg, p.deg2rad);

@@ -182,56 +182,103 @@ size_t pose_scan_state_bytes() { return sizeof(ScanState); }
 // ray set-up
 // ===========================================================================
 //
-// grid.x = n_flights * groups_per_flight; block = 1024 = 32 frames x 32 beams.
+// TMA (bulk async copy) + mbarrier: the 4 KB of range readings of a block's 32 frames are one contiguous
+// span of the log; one thread starts the copy into shared memory, every warp picks its 128 bytes up there.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "UQS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra UQS_WAIT;\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// grid = (groups_per_flight, n_flights); block = 1024 = 32 frames x 32 beams.
 // kind == nullptr: every entry is a frame (pose + 32 ranges).
 // kind[i] == 1   : entry i is one raw ray raycast_update(x0,y0,x1,y1,hit) stored as
 //                  x=x0, y=y0, yaw=x1, ranges[0]=y1, ranges[1]=hit (drop-in symbol only).
 __global__ void __launch_bounds__(1024, 2)
-k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __restrict__ x,
+k_ray_setup(const __grid_constant__ DevParams p, int n_frames, const float* __restrict__ x,
             const float* __restrict__ y, const float* __restrict__ yaw_deg,
             const float* __restrict__ ranges, const uint8_t* __restrict__ kind, int want_k0,
             const uint32_t* __restrict__ inv_table, uint4* __restrict__ frames, uint2* __restrict__ groups, uint2* __restrict__ rays,
             unsigned long long* __restrict__ stats /* [4]: U, accepted, skipped, domain */) {
+  __shared__ __align__(128) float s_rng[32 * 32];
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_box[4][32];
-  __shared__ unsigned long long s_cnt[4][32];
+  __shared__ unsigned s_cnt[2][32];
+  __shared__ int s_org[32][2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int flight = blockIdx.x / groups_per_flight;
-  const int g = blockIdx.x % groups_per_flight;
+  const int flight = blockIdx.y, g = blockIdx.x, groups_per_flight = gridDim.x;
   const int f = g * 32 + w;
   const size_t fbase = (size_t)flight * n_frames;
+  const int nfr = min(32, n_frames - g * 32);                     // frames of this block
+
+  // stage the block's range readings: one bulk copy (needs 16-byte alignment; plain loads otherwise)
+  const float* blk_ranges = ranges + (fbase + (size_t)g * 32) * 32;
+  const bool staged = (reinterpret_cast<size_t>(ranges) & 15) == 0;
+  const uint32_t bar_sa = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  if (staged) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar_sa, 1);
+      bulk_load_g2s((uint32_t)__cvta_generic_to_shared(s_rng), blk_ranges, (uint32_t)nfr * 128u, bar_sa);
+    }
+    __syncthreads();                                               // the barrier object is visible to every waiter
+  }
 
   int xmin = 0x7fff, xmax = 0, ymin = 0x7fff, ymax = 0;
-  unsigned long long cells = 0;
+  unsigned cells = 0;
   int accepted = 0, skipped = 0, domain = 0;
 
-  // the start cell is per frame, not per beam: warp 0 computes it for the block's 32 frames (lane = frame)
-  __shared__ int s_org[32][2];
-  if (w == 0) {
+  // the start cell is per frame, not per beam: the last warp computes it for the block's 32 frames
+  // (lane = frame) while the others are busy with their end points
+  if (w == 31) {
     int ox = -1, oy = -1;
     const int fo = g * 32 + lane;
     if (fo < n_frames && !world_to_grid(p, x[fbase + fo], y[fbase + fo], ox, oy)) ox = oy = -1;
     s_org[lane][0] = ox;
     s_org[lane][1] = oy;
   }
-  __syncthreads();
 
-  if (f < n_frames) {
-    const size_t fi = fbase + f;
+  // end point of the beam (everything that does not need the start cell) before the block barrier
+  const bool live = f < n_frames;
+  const size_t fi = fbase + (live ? f : 0);
+  float ex = 0.f, ey = 0.f;
+  bool hit = false, raw = false;
+  int st = 0;
+  if (live) {
     const float px = x[fi], py = y[fi], third = yaw_deg[fi];
-    const bool raw = kind != nullptr && kind[fi] == 1;
-    const int gx0 = s_org[w][0], gy0 = s_org[w][1];
-    const bool have_o = gx0 >= 0;
-    float ex = 0.f, ey = 0.f;
-    bool hit = false;
-    int st;
+    raw = kind != nullptr && kind[fi] == 1;
+    if (staged) mbar_wait(bar_sa, 0);
+    const float* rr = staged ? &s_rng[w * 32] : &ranges[fi * 32];
     if (!raw) {
-      st = beam_endpoint(p, px, py, third, ranges[fi * 32 + lane], lane, ex, ey, hit);
+      st = beam_endpoint(p, px, py, third, rr[lane], lane, ex, ey, hit);
     } else {
       st = (lane == 0) ? 1 : 0;
       ex = third;
-      ey = ranges[fi * 32 + 0];
-      hit = ranges[fi * 32 + 1] != 0.0f;
+      ey = rr[0];
+      hit = rr[1] != 0.0f;
     }
+  }
+  __syncthreads();
+
+  if (live) {
+    const int gx0 = s_org[w][0], gy0 = s_org[w][1];
+    const bool have_o = gx0 >= 0;
     uint32_t w0 = 0, w1 = 0;
     if (st < 0) {
       domain = 1;
@@ -248,7 +295,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
           w1 = __ldg(&inv_table[m]);                           // ceil(2^31 / m), 0 for m == 0
           xmin = min(gx0, gx1); xmax = max(gx0, gx1);
           ymin = min(gy0, gy1); ymax = max(gy0, gy1);
-          cells = (unsigned long long)m + 1;
+          cells = (unsigned)m + 1u;
           accepted = 1;
         }
       }
@@ -273,7 +320,7 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
       float ra, rb;
       if (xmaj) { ra = xpos ? (ypos ? 0.f : 8.f) : 4.f; rb = (xpos == ypos) ? 1.f : -1.f; }
       else      { ra = ypos ? 2.f : 6.f;                rb = (xpos == ypos) ? -1.f : 1.f; }
-      float sigma = (m > 0) ? ra + rb * ((float)n / (float)m) : 0.f;
+      float sigma = (m > 0) ? ra + rb * __fdividef((float)n, (float)m) : 0.f;   // feeds the conservative K0 only
       if (sigma >= 8.f) sigma -= 8.f;
       const int mmax = __reduce_max_sync(0xffffffffu, m);
       const unsigned any = __ballot_sync(0xffffffffu, m >= 0);
@@ -336,14 +383,12 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
                               (uint32_t)xmin | ((uint32_t)xmax << 16),
                               (uint32_t)ymin | ((uint32_t)ymax << 16));
   }
-  // per-warp counters, then one block-level reduce by warp 0
-  unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)accepted);
-  unsigned s = __reduce_add_sync(0xffffffffu, (unsigned)skipped);
-  unsigned d = __reduce_add_sync(0xffffffffu, (unsigned)domain);
-  unsigned c32 = __reduce_add_sync(0xffffffffu, (unsigned)cells);   // <= 32*1025 per warp
+  // per-warp counters (two packed words), then one block-level reduce by warp 0
+  const unsigned as = __reduce_add_sync(0xffffffffu, (unsigned)accepted | ((unsigned)skipped << 16));
+  const unsigned cd = __reduce_add_sync(0xffffffffu, cells | ((unsigned)domain << 21));       // cells <= 32*1025 per warp
   if (lane == 0) {
     s_box[0][w] = xmin; s_box[1][w] = xmax; s_box[2][w] = ymin; s_box[3][w] = ymax;
-    s_cnt[0][w] = c32; s_cnt[1][w] = a; s_cnt[2][w] = s; s_cnt[3][w] = d;
+    s_cnt[0][w] = as; s_cnt[1][w] = cd;
   }
   __syncthreads();
   if (w == 0) {
@@ -351,12 +396,15 @@ k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* __res
     const int bx1 = __reduce_max_sync(0xffffffffu, s_box[1][lane]);
     const int by0 = __reduce_min_sync(0xffffffffu, s_box[2][lane]);
     const int by1 = __reduce_max_sync(0xffffffffu, s_box[3][lane]);
+    const unsigned bas = __reduce_add_sync(0xffffffffu, s_cnt[0][lane]);                        // <= 1024 per field
+    const unsigned long long bcd = s_cnt[1][lane];
+    const unsigned bc = __reduce_add_sync(0xffffffffu, (unsigned)(bcd & 0x1fffffu));            // <= 1024*1025 < 2^21
+    const unsigned bd = __reduce_add_sync(0xffffffffu, (unsigned)(bcd >> 21));
     if (lane == 0)
       groups[(size_t)flight * groups_per_flight + g] =
           make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
     if (lane < 4) {
-      unsigned long long t = 0;
-      for (int i = 0; i < 32; i++) t += s_cnt[lane][i];
+      const unsigned long long t = lane == 0 ? bc : (lane == 1 ? (bas & 0xffffu) : (lane == 2 ? (bas >> 16) : bd));
       if (t) atomicAdd(&stats[lane], t);
     }
   }

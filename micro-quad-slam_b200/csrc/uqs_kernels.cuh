@@ -60,7 +60,7 @@ int pose_scan_tile();
 size_t pose_scan_state_bytes();
 int pose_scan_threads();
 
-__global__ void k_ray_setup(DevParams p, int n_frames, int groups_per_flight, const float* x,
+__global__ void k_ray_setup(const __grid_constant__ DevParams p, int n_frames, const float* x,
                             const float* y, const float* yaw_deg, const float* ranges,
                             const uint8_t* kind, int want_k0, const uint32_t* inv_table, uint4* frames, uint2* groups,
                             uint2* rays,
