@@ -104,6 +104,11 @@ unsigned long long uqs_kernel_launches(void);
  * call -- [0] pose integration, [1] ray set-up, [2] replay -- and synchronises. */
 int  uqs_set_profiling(int on);
 int  uqs_profile_collect(double ms[3], int counts[3]);
+/* Timeline of the spans recorded since the last uqs_profile_collect(): out[3*i] = kind (0 pose,
+ * 1 ray set-up, 2 replay, 3 H2D copy, 4 D2H copy of the host-buffer pipeline), out[3*i+1] and
+ * out[3*i+2] = start and end in ms after the first span's start.  Returns the number of spans
+ * written (<= max_spans, -1 when not initialised); does not clear them; synchronises the device. */
+int  uqs_profile_timeline(double* out, int max_spans);
 /* Block until everything enqueued so far has finished. */
 int  uqs_sync(void);
 

@@ -80,7 +80,7 @@ _EXPORTS = [
     # batch API
     "uqs_params_default", "uqs_init", "uqs_shutdown", "uqs_last_error", "uqs_device_sm_count",
     "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_kernel_launches",
-    "uqs_set_profiling", "uqs_profile_collect", "uqs_set_host_chunk",
+    "uqs_set_profiling", "uqs_profile_collect", "uqs_profile_timeline", "uqs_set_host_chunk",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
     "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
     "uqs_beams_from_scans", "uqs_beams_from_scans_dev", "uqs_replay_recentering", "uqs_frontier_scores",
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
     L.uqs_set_engine.argtypes = [ip, ip]
     L.uqs_set_profiling.argtypes = [ip]
     L.uqs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.uqs_profile_timeline.argtypes = [C.POINTER(C.c_double), ip]
     L.uqs_kernel_launches.restype = C.c_ulonglong
     L.uqs_pose_integrate.argtypes = [ip, ip] + [vp] * 8 + [ip]
     L.uqs_pose_integrate_dev.argtypes = [ip, ip] + [vp] * 8 + [ip]
@@ -194,6 +195,14 @@ def profile_collect():
     ms, cnt = (C.c_double * 3)(), (C.c_int * 3)()
     _check(lib().uqs_profile_collect(ms, cnt))
     return list(ms), list(cnt)
+
+
+def profile_timeline(max_spans: int = 4096):
+    """[(kind, start_ms, end_ms)] of the spans recorded since the last profile_collect(); kinds 0 pose, 1 ray
+    set-up, 2 replay, 3 H2D, 4 D2H."""
+    buf = (C.c_double * (3 * max_spans))()
+    n = lib().uqs_profile_timeline(buf, max_spans)
+    return [(int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i in range(max(n, 0))]
 
 
 def kernel_launches() -> int:

@@ -137,6 +137,12 @@ static void choose_tiles(int W, int rows, int target, int* sw, int* sh, int* nsx
   pick(rows, g_ctx.tune_sh, target >= 80 ? target + target / 4 : target, sh, nsy);
 }
 
+// zero fill by a kernel of ours (counted like every other launch)
+static cudaError_t zero_counted(void* p, size_t bytes, cudaStream_t st) {
+  g_ctx.launches += bytes ? 1 : 0;
+  return zero_async(p, bytes, st);
+}
+
 int replay_device(const DevParams& dp, int n_flights, int n_frames, const float* x, const float* y,
                   const float* yaw, const float* ranges, const uint8_t* kind, int8_t* grids,
                   int accumulate, int row0, int rows, bool reset_stats) {
@@ -197,8 +203,9 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   // after the ray set-up of a chunk (k_flight_boxes), so the choice is made per chunk below.
   // warps per resident CTA (measured): 4 when there are flights for every CTA slot of every SM -- per-frame
   // bookkeeping is paid per warp -- more warps per CTA when flights are scarce
+  // (chunks of the host-buffer pipeline overlap on two streams and fill the chip together: 4 as well)
   const int nw = g_ctx.flight_warps ? g_ctx.flight_warps
-                                    : (n_flights >= 4 * g_ctx.sm_count ? 4 : (n_flights >= 2 * g_ctx.sm_count ? 8 : 16));
+                 : ((n_flights >= 4 * g_ctx.sm_count || g_ctx.w != &g_ctx.works[0]) ? 4 : (n_flights >= 2 * g_ctx.sm_count ? 8 : 16));
   const bool may_reside = g_ctx.engine != 1 && row0 == 0 && rows == dp.H;
   if (g_ctx.engine == 2 && !may_reside) {
     set_error("engine 2 (resident) cannot replay a row band");
@@ -222,7 +229,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   unsigned long long* counters = (unsigned long long*)g_ctx.w->counters.p;   // [0..3] stats, [8+] job counters
   cudaError_t e;
   if (reset_stats) {
-    e = cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), st);
+    e = zero_counted(counters, 8 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return cuda_fail(e, "memset stats");
   }
 
@@ -248,14 +255,19 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       // touched bounding box per flight -> shared memory per CTA -> CTAs per SM -> engine choice
       if ((rc = g_ctx.w->boxes.ensure((size_t)nf * sizeof(int4)))) return rc;
       int* d_dims = (int*)(counters + 32);
-      e = cudaMemsetAsync(d_dims, 0, 2 * sizeof(int), st);
+      if (!g_ctx.w->h_dims) {
+        e = cudaHostAlloc((void**)&g_ctx.w->h_dims, 16, cudaHostAllocMapped);
+        if (e != cudaSuccess) { g_ctx.w->h_dims = nullptr; return cuda_fail(e, "cudaHostAlloc(dims)"); }
+      }
+      int* h_dims_dev = nullptr;
+      e = cudaHostGetDevicePointer((void**)&h_dims_dev, g_ctx.w->h_dims, 0);
+      if (e == cudaSuccess) e = zero_counted(d_dims, 2 * sizeof(int), st);
       if (e == cudaSuccess)
-        e = flight_boxes_launch(nf, gpf, (const uint2*)g_ctx.w->groups.p, dp.W, dp.H, (int4*)g_ctx.w->boxes.p, d_dims, st);
-      int dims[2] = { 0, 0 };
-      if (e == cudaSuccess) e = cudaMemcpyAsync(dims, d_dims, sizeof(dims), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        e = flight_boxes_launch(nf, gpf, (const uint2*)g_ctx.w->groups.p, dp.W, dp.H, (int4*)g_ctx.w->boxes.p, d_dims, h_dims_dev, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // the launch geometry of the replay depends on the boxes
       if (e != cudaSuccess) return cuda_fail(e, "k_flight_boxes");
-      g_ctx.launches += 1;
+      const int dims[2] = { g_ctx.w->h_dims[0], g_ctx.w->h_dims[1] };
+      g_ctx.launches += 2;                                     // boxes, publish
       const int bw = std::max(dims[0], 4), bh = std::max(dims[1], 1);
       int fpitch = (bw + 3) & ~3;
       if (((fpitch >> 2) & 1) == 0) fpitch += 4;
@@ -275,7 +287,9 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       }
       // auto: resident when several CTAs fit an SM (barrier stalls of one hide behind the others) and there is at
       // least a flight per SM (measured crossover); otherwise the sub-tile engine (time-sliced when flights are few)
-      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || (f_ctas >= 2 && nf >= g_ctx.sm_count));
+      // (a chunk of the host-buffer pipeline shares the chip with its neighbours: no flight-count condition there)
+      const bool pipelined = g_ctx.w != &g_ctx.works[0];
+      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || (f_ctas >= 2 && (nf >= g_ctx.sm_count || pipelined)));
       if (resident) {
         FlightArgs FA;
         FA.frames = (const uint4*)g_ctx.w->frames.p;
@@ -288,9 +302,9 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         FA.lo_free = dp.lo_free; FA.lo_occ = dp.lo_occ; FA.lo_min = dp.lo_min; FA.lo_max = dp.lo_max;
         FA.end_nohit = dp.end_nohit;
         FA.accumulate = accumulate;
-        e = cudaMemsetAsync(FA.job_counter, 0, sizeof(unsigned long long), st);
+        e = zero_counted(FA.job_counter, sizeof(unsigned long long), st);
         // cells outside a flight's box are never touched: they are zero in a fresh replay
-        if (e == cudaSuccess && !accumulate) e = cudaMemsetAsync(FA.grids, 0, (size_t)nf * dp.W * dp.H, st);
+        if (e == cudaSuccess && !accumulate) e = zero_counted(FA.grids, (size_t)nf * dp.W * dp.H, st);
         if (e != cudaSuccess) return cuda_fail(e, "memset before k_replay_flights");
         const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)f_ctas * g_ctx.sm_count);
         KernelTimer t_rep(2);
@@ -340,7 +354,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     A.lo_free = dp.lo_free; A.lo_occ = dp.lo_occ; A.lo_min = dp.lo_min; A.lo_max = dp.lo_max;
     A.end_nohit = dp.end_nohit;
     A.accumulate = accumulate;
-    e = cudaMemsetAsync(A.job_counter, 0, sizeof(unsigned long long), st);
+    e = zero_counted(A.job_counter, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return cuda_fail(e, "memset job counter");
     unsigned long long want = (A.total_jobs + kReplayWarps - 1) / kReplayWarps;
     unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctas_per_sm * g_ctx.sm_count);
@@ -401,7 +415,7 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
   float* inc_n = (float*)g_ctx.w->inc.p;
   float* inc_e = inc_n + total;
   unsigned long long* dom = (unsigned long long*)g_ctx.w->counters.p + 16;
-  cudaError_t e = cudaMemsetAsync(dom, 0, sizeof(unsigned long long), st);
+  cudaError_t e = zero_counted(dom, sizeof(unsigned long long), st);
   if (e != cudaSuccess) return cuda_fail(e, "memset pose counter");
   volatile float pi_f = (float)M_PI;
   const float deg2rad = pi_f / 180.0f;
@@ -554,12 +568,31 @@ int uqs_profile_collect(double ms[3], int counts[3]) {
   for (int i = 0; i < 3; i++) { ms[i] = 0.0; counts[i] = 0; }
   for (auto& s : g_ctx.spans) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ms[s.kind] += t; counts[s.kind]++; }
+    if (s.kind < 3 && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ms[s.kind] += t; counts[s.kind]++; }
     cudaEventDestroy(s.a);
     cudaEventDestroy(s.b);
   }
   g_ctx.spans.clear();
   return UQS_OK;
+}
+
+/* Timeline of the spans recorded since the last uqs_profile_collect(): out[3*i] = kind (0 pose, 1 ray set-up,
+ * 2 replay, 3 H2D, 4 D2H), out[3*i+1], out[3*i+2] = start, end in ms after the first span's start.  Returns the
+ * number of spans written (at most max_spans); does not clear them.  Synchronises the device. */
+int uqs_profile_timeline(double* out, int max_spans) {
+  int rc = check_ready();
+  if (rc) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess || g_ctx.spans.empty() || !out) return 0;
+  int n = 0;
+  const cudaEvent_t ref = g_ctx.spans[0].a;
+  for (auto& s : g_ctx.spans) {
+    if (n >= max_spans) break;
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, ref, s.a) != cudaSuccess || cudaEventElapsedTime(&t1, ref, s.b) != cudaSuccess) continue;
+    out[3 * n] = s.kind; out[3 * n + 1] = t0; out[3 * n + 2] = t1;
+    n++;
+  }
+  return n;
 }
 
 int uqs_replay_dev(const uqs_params* p, int n_flights, int n_frames, const float* x, const float* y,

@@ -24,7 +24,10 @@ struct Work {
   DevBuf rays, frames, groups, counters, inc, scan, order, maps, boxes;
   int order_nsx = 0, order_nsy = 0;             // geometry the cached tile order was built for
   cudaStream_t stream = nullptr;
+  int* h_dims = nullptr;                        // mapped host words the box kernel publishes its maxima to
   void release() {
+    if (h_dims) cudaFreeHost(h_dims);
+    h_dims = nullptr;
     DevBuf* all[] = { &rays, &frames, &groups, &counters, &inc, &scan, &order, &maps, &boxes };
     order_nsx = order_nsy = 0;
     for (DevBuf* b : all) b->release();
@@ -53,7 +56,7 @@ struct Context {
 
   // optional per-kernel timing (uqs_set_profiling): event pairs on the launching stream
   bool profiling = false;
-  struct Span { cudaEvent_t a, b; int kind; };   // kind 0 pose, 1 ray set-up, 2 replay
+  struct Span { cudaEvent_t a, b; int kind; };   // kind 0 pose, 1 ray set-up, 2 replay, 3 H2D, 4 D2H (pipeline copies)
   std::vector<Span> spans;
 
   cudaStream_t stream() const { return w->stream ? w->stream : (use_ext ? ext_stream : own_stream); }
@@ -88,14 +91,15 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
 // RAII-free helper: records an event pair around a kernel launch when profiling is on
 struct KernelTimer {
   int kind;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  explicit KernelTimer(int k) : kind(k) {
+  explicit KernelTimer(int k, cudaStream_t on = nullptr) : kind(k), st(on ? on : g_ctx.stream()) {
     if (g_ctx.profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess)
-      cudaEventRecord(a, g_ctx.stream());
+      cudaEventRecord(a, st);
   }
   void stop() {
     if (a && b) {
-      cudaEventRecord(b, g_ctx.stream());
+      cudaEventRecord(b, st);
       g_ctx.spans.push_back({a, b, kind});
     }
   }

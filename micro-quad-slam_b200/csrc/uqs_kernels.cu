@@ -15,6 +15,8 @@
 // (d,c) order, and the cells of one ray are distinct, so the 32 lanes of the warp
 // can apply one ray's cells at once with plain byte read-modify-writes -- no
 // atomics, no races, bit-identical to the sequential loop.
+#include <algorithm>
+
 #include "uqs_kernels.cuh"
 
 namespace uqs {
@@ -1051,9 +1053,18 @@ static void (*flight_kernel(int nw))(FlightArgs) {
   return nw == 4 ? k_replay_flights<4> : (nw == 8 ? k_replay_flights<8> : (nw == 32 ? k_replay_flights<32> : k_replay_flights<16>));
 }
 
+// dims -> mapped host memory: a device-to-host memcpy of these two words would queue on the D2H copy engine
+// behind the grids of the previous chunk (measured: 1.8 ms per chunk of the host-buffer pipeline)
+__global__ void k_publish_dims(const int* __restrict__ dims, volatile int* host_dims) {
+  host_dims[0] = dims[0];
+  host_dims[1] = dims[1];
+  __threadfence_system();
+}
+
 cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint2* groups, int W, int H, int4* boxes,
-                                int* dims, cudaStream_t st) {
+                                int* dims, int* host_dims_dev, cudaStream_t st) {
   k_flight_boxes<<<(unsigned)((n_flights + 3) / 4), 128, 0, st>>>(n_flights, groups_per_flight, groups, W, H, boxes, dims);
+  k_publish_dims<<<1, 1, 0, st>>>(dims, host_dims_dev);
   return cudaGetLastError();
 }
 
@@ -1065,6 +1076,28 @@ cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm) {
 
 cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A) {
   flight_kernel(nw)<<<grid, nw * 32, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+// Zero fill as a kernel.  cudaMemsetAsync of a large range can be carried out by a copy engine, where it
+// queues behind the D2H of the previous chunk of the host-buffer pipeline (measured: every replay waited
+// ~1.8 ms for the neighbouring stream's copy); a kernel only depends on its own stream.
+__global__ void k_zero(unsigned char* __restrict__ p, size_t bytes) {
+  const size_t head = min(bytes, (size_t)((16 - (reinterpret_cast<size_t>(p) & 15)) & 15));
+  const size_t n16 = (bytes - head) >> 4;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  uint4* q = reinterpret_cast<uint4*>(p + head);
+  for (size_t i = tid; i < n16; i += nth) q[i] = make_uint4(0u, 0u, 0u, 0u);
+  const size_t tail0 = head + (n16 << 4);
+  if (tid < head) p[tid] = 0;
+  if (tid < bytes - tail0) p[tail0 + tid] = 0;
+}
+
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  const size_t want = (bytes / 16 + 255) / 256;
+  const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(want, 1), 148 * 16);
+  k_zero<<<blocks, 256, 0, st>>>(reinterpret_cast<unsigned char*>(p), bytes);
   return cudaGetLastError();
 }
 

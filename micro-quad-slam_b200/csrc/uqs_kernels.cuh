@@ -58,6 +58,7 @@ __global__ void k_pose_scan(int n_flights, int n_samples, int parts_per_flight, 
                             unsigned int* ticket);
 int pose_scan_tile();
 size_t pose_scan_state_bytes();
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st);   // zero fill by a kernel (never a copy engine)
 int pose_scan_threads();
 
 __global__ void k_ray_setup(const __grid_constant__ DevParams p, int n_frames, const float* x,
@@ -73,7 +74,7 @@ __global__ void k_replay_tiles(ReplayArgs A);
 __global__ void k_compose_slices(int8_t* grids, const uint32_t* maps, int n_flights, int W, int H, int S, int row0,
                                  int rows);
 cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint2* groups, int W, int H, int4* boxes,
-                                int* dims, cudaStream_t st);
+                                int* dims, int* host_dims_dev, cudaStream_t st);
 cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm);
 cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);

@@ -1,8 +1,10 @@
 // uqs_pipeline.cu -- host-buffer entry points (uqs_replay, uqs_replay_flow).
 //
-// The caller's logs live in host memory; the work is cut into chunks of flights and the three
-// stages of a chunk run on three streams, double-buffered, so that PCIe traffic hides behind the
-// kernels:   H2D(c+1)  ||  P0 + ray set-up + replay (c)  ||  D2H(c-1)
+// The caller's logs live in host memory; the work is cut into chunks of flights whose three steps run on
+// separate streams so that PCIe traffic hides behind the kernels:
+//     H2D(c+1..c+3)  ||  P0 + ray set-up + replay (c, c+1 on two alternating streams)  ||  D2H(c-1)
+// Four staging buffers rotate: the copy engine runs up to three chunks ahead of the kernels (with two, the
+// H2D of chunk c+1 had to wait for the kernels of chunk c-1 and the copy engine idled a quarter of the time).
 // Copies overlap only from page-locked host memory (cudaHostRegister / cudaHostAlloc / torch
 // pin_memory); pageable buffers still work, serialised by the driver.
 #include <algorithm>
@@ -14,7 +16,9 @@ namespace uqs {
 
 namespace {
 
-struct Stage {                 // device staging of one chunk (two of them alternate)
+constexpr int kStages = 4;
+
+struct Stage {                 // device staging of one chunk (kStages of them rotate)
   DevBuf t, rx, ry, h, yaw, q, x, y, ranges, grids;
   cudaEvent_t in_ready = nullptr, computed = nullptr, out_done = nullptr;
 };
@@ -22,7 +26,7 @@ struct Stage {                 // device staging of one chunk (two of them alter
 struct Pipeline {
   bool made = false;
   cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = { nullptr, nullptr };
-  Stage st[2];
+  Stage st[kStages];
 } P;
 
 int pipeline_init() {
@@ -31,7 +35,7 @@ int pipeline_init() {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P.s_cmp[0], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P.s_cmp[1], cudaStreamNonBlocking);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+  for (int i = 0; i < kStages && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&P.st[i].in_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.st[i].computed, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.st[i].out_done, cudaEventDisableTiming);
@@ -73,19 +77,23 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   if (rc) return rc;
   const bool flow = L.t_ms != nullptr;
   const size_t cells = (size_t)p->W * p->H;
-  // Chunk schedule: chunks of ~5 flights per SM after a short ramp (measured on the 4096-flight ensemble: smaller
-  // chunks leave CTA slots empty, larger ones expose more of the first H2D and the last D2H).
+  // Chunk schedule: body chunks of 4 flights per SM (one full wave of resident replay CTAs on the 400x400
+  // ensemble), after a short ramp up (1, 2 flights per SM: their H2D cannot hide behind any kernel) and before a
+  // short ramp down (2, 1: the last chunk's kernels and D2H hide behind nothing).
   std::vector<int> starts;                      // flight index where chunk c begins; starts.back() = n_flights
   {
-    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 5 * g_ctx.sm_count;
-    if ((size_t)chunk_cap * n_frames * 152 > ((size_t)3 << 30))           // bound the staging buffers (2 x chunk)
-      chunk_cap = std::max<int>(1, (int)(((size_t)3 << 30) / ((size_t)n_frames * 152)));
-    if (g_ctx.host_chunk == 0 && n_flights >= 3 * chunk_cap) {
-      // ramp: 1 then 2 flights per SM first (their H2D cannot hide behind any kernel), then full chunks
+    const int sm = g_ctx.sm_count;
+    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 4 * sm;
+    const size_t stage_budget = (size_t)6 << 30;                          // bound the staging buffers (kStages x chunk)
+    if ((size_t)chunk_cap * n_frames * 152 * kStages > stage_budget)
+      chunk_cap = std::max<int>(1, (int)(stage_budget / ((size_t)n_frames * 152 * kStages)));
+    if (g_ctx.host_chunk == 0 && chunk_cap == 4 * sm && n_flights >= 12 * sm) {
       int f = 0;
-      for (int c : { g_ctx.sm_count, 2 * g_ctx.sm_count }) { starts.push_back(f); f += c; }
-      const int body = n_flights - f, n_mid = (body + chunk_cap - 1) / chunk_cap;
+      for (int c : { sm, 2 * sm }) { starts.push_back(f); f += c; }
+      const int body = n_flights - f - 3 * sm, n_mid = (body + chunk_cap - 1) / chunk_cap;
       for (int i = 0; i < n_mid; i++) starts.push_back(f + (int)((long long)body * i / n_mid));
+      starts.push_back(n_flights - 3 * sm);
+      starts.push_back(n_flights - sm);
     } else {
       const int n_want = (n_flights + chunk_cap - 1) / chunk_cap;
       for (int i = 0; i < n_want; i++) starts.push_back((int)((long long)n_flights * i / n_want));
@@ -106,7 +114,7 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
     ~WorkScope() { g_ctx.w = &g_ctx.works[0]; }
   };
 
-  for (int i = 0; i < std::min(2, n_chunks); i++) {
+  for (int i = 0; i < std::min(kStages, n_chunks); i++) {
     Stage& S = P.st[i];
     const size_t n = (size_t)chunk * n_frames;
     if (flow && ((rc = S.t.ensure(n * 4)) || (rc = S.rx.ensure(n * 4)) || (rc = S.ry.ensure(n * 4)) ||
@@ -118,11 +126,12 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   }
 
   auto upload = [&](int c) -> cudaError_t {
-    Stage& S = P.st[c & 1];
+    Stage& S = P.st[c % kStages];
     const int f0 = starts[c], nf = starts[c + 1] - f0;
     const size_t o = (size_t)f0 * n_frames, n = (size_t)nf * n_frames;
     cudaError_t r = cudaSuccess;
-    if (c >= 2) r = cudaStreamWaitEvent(P.s_in, P.st[c & 1].computed, 0);     // inputs of chunk c-2 consumed
+    if (c >= kStages) r = cudaStreamWaitEvent(P.s_in, S.computed, 0);         // inputs of chunk c-kStages consumed
+    KernelTimer t_in(3, P.s_in);
     auto cp = [&](DevBuf& b, const void* src, size_t bytes) {
       if (r == cudaSuccess) r = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, P.s_in);
     };
@@ -134,20 +143,24 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
     }
     cp(S.yaw, L.yaw + o, n * 4);
     cp(S.ranges, L.ranges + o * 32, n * 128);
+    t_in.stop();
     if (r == cudaSuccess) r = cudaEventRecord(S.in_ready, P.s_in);
     return r;
   };
 
-  if ((e = upload(0)) != cudaSuccess) return cuda_fail(e, "H2D");
+  // upload(c') waits for the kernels of chunk c'-kStages, so it can only be queued once those are: the copies
+  // of chunks 0..kStages-2 go first, then iteration c queues the copy of chunk c+kStages-1
+  for (int c = 0; c < std::min(kStages - 1, n_chunks); c++)
+    if ((e = upload(c)) != cudaSuccess) return cuda_fail(e, "H2D");
   for (int c = 0; c < n_chunks; c++) {
-    Stage& S = P.st[c & 1];
+    Stage& S = P.st[c % kStages];
     const int f0 = starts[c], nf = starts[c + 1] - f0;
     const size_t o = (size_t)f0 * n_frames, n = (size_t)nf * n_frames;
-    if (c + 1 < n_chunks && (e = upload(c + 1)) != cudaSuccess) return cuda_fail(e, "H2D");
+    if (c + kStages - 1 < n_chunks && (e = upload(c + kStages - 1)) != cudaSuccess) return cuda_fail(e, "H2D");
     WorkScope scope(c & 1);
     cudaStream_t sc = P.s_cmp[c & 1];
     if ((e = cudaStreamWaitEvent(sc, S.in_ready, 0)) != cudaSuccess) return cuda_fail(e, "wait H2D");
-    if (c >= 2 && (e = cudaStreamWaitEvent(sc, S.out_done, 0)) != cudaSuccess) return cuda_fail(e, "wait D2H");   // grid buffer free
+    if (c >= kStages && (e = cudaStreamWaitEvent(sc, S.out_done, 0)) != cudaSuccess) return cuda_fail(e, "wait D2H");   // grid buffer free
     if (flow) {
       if ((rc = pose_device(nf, n_frames, (uint32_t*)S.t.p, (float*)S.rx.p, (float*)S.ry.p, (float*)S.h.p, (float*)S.yaw.p,
                             (uint8_t*)S.q.p, (float*)S.x.p, (float*)S.y.p, 0)))
@@ -158,11 +171,13 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
       return rc;
     if ((e = cudaEventRecord(S.computed, sc)) != cudaSuccess) return cuda_fail(e, "record");
     if ((e = cudaStreamWaitEvent(P.s_out, S.computed, 0)) != cudaSuccess) return cuda_fail(e, "wait compute");
+    KernelTimer t_out(4, P.s_out);
     e = cudaMemcpyAsync(grids_out + (size_t)f0 * cells, S.grids.p, (size_t)nf * cells, cudaMemcpyDeviceToHost, P.s_out);
     if (e == cudaSuccess && flow && L.pox && L.poy) {
       e = cudaMemcpyAsync(L.pox + o, S.x.p, n * 4, cudaMemcpyDeviceToHost, P.s_out);
       if (e == cudaSuccess) e = cudaMemcpyAsync(L.poy + o, S.y.p, n * 4, cudaMemcpyDeviceToHost, P.s_out);
     }
+    t_out.stop();
     if (e == cudaSuccess) e = cudaEventRecord(S.out_done, P.s_out);
     if (e != cudaSuccess) return cuda_fail(e, "D2H");
   }
