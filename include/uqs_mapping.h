@@ -225,6 +225,15 @@ long uqs_scanlog_read(const char* path, int keep_nan_pose, long max_records, uin
                       uint8_t* of_q, uint8_t* kf_flags, uint8_t* grid_raw);
 long uqs_scanlog_count(const char* path, int keep_nan_pose);
 
+/* N4: reader of navlog.csv (header uav_local_nav.c:1489-1494, rows :1586-1625): 22 text columns per log tick,
+ * "nan" for missing values, flights appended without further headers, a truncated last row is dropped.  Fills
+ * the columns P0 and the mapper consume; any output may be NULL; t_ms keeps the low 32 bits of the 64-bit
+ * millisecond clock.  Returns the number of well-formed rows in the file (call with max_rows = 0 to size the
+ * buffers), -1 if the file cannot be opened. */
+long uqs_navlog_read(const char* path, long max_rows, uint32_t* t_ms, float* yaw_deg, float* alt_m, float* x_m,
+                     float* y_m, float* vx_mps, float* vy_mps, float* rf_m, uint8_t* of_q, float* of_rate_x,
+                     float* of_rate_y, float* tof4);
+
 /* Measured on-chip read-modify-write ceiling: every warp of a full grid does
  * conflict-free byte RMWs on its shared-memory sub-tile.  Returns updates/s. */
 int uqs_measure_rmw_peak(double* updates_per_s);

@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuqs_mapping.so")
+LIB_PATH = os.environ.get("UQS_LIBRARY") or os.path.join(_HERE, "libuqs_mapping.so")   # override: kernel-variant experiments (tools/)
 SYNTH_LIB_PATH = os.path.join(_HERE, "libuqs_synth.so")
 
 BEAMS_PER_FRAME = 32
@@ -84,7 +84,7 @@ _EXPORTS = [
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
     "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
     "uqs_beams_from_scans", "uqs_beams_from_scans_dev", "uqs_replay_recentering", "uqs_frontier_scores",
-    "uqs_scanlog_read", "uqs_scanlog_count", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
+    "uqs_scanlog_read", "uqs_scanlog_count", "uqs_navlog_read", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
     # drop-in symbols
     "uqs_dropin_configure", "uqs_dropin_flush", "uqs_dropin_upload", "map_reset",
     "occ_grid", "map_inited", "map_origin_x", "map_origin_y", "tof_beams_m", "pending_kf_flags",
@@ -130,6 +130,8 @@ def lib() -> C.CDLL:
     L.uqs_scanlog_read.argtypes = [C.c_char_p, ip, C.c_long] + [vp] * 11
     L.uqs_scanlog_count.restype = C.c_long
     L.uqs_scanlog_count.argtypes = [C.c_char_p, ip]
+    L.uqs_navlog_read.restype = C.c_long
+    L.uqs_navlog_read.argtypes = [C.c_char_p, C.c_long] + [vp] * 12
     L.map_recenter_shift.argtypes = [ip, ip]
     L.map_recenter_shift.restype = None
     L.map_recentre_if_needed.argtypes = [C.c_float, C.c_float]
@@ -338,6 +340,22 @@ def frontier_scores(p: Params, grid, x, y, yaw_deg, offset_deg):
     out = np.empty(x.size, np.int32)
     _check(lib().uqs_frontier_scores(C.byref(p), _ptr(g), x.size, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(offset_deg), _ptr(out)))
     return out
+
+
+def navlog_read(path: str) -> dict:
+    """N4: navlog.csv -> SoA numpy arrays (the columns P0 and the mapper consume; host file I/O in the C library)."""
+    L = lib()
+    n = L.uqs_navlog_read(path.encode(), 0, *([None] * 12))
+    if n < 0:
+        raise UqsError(ERR_BAD_ARG, f"cannot read nav log {path} (code {n})")
+    f32 = ("yaw_deg", "alt_m", "x_m", "y_m", "vx_mps", "vy_mps", "rf_m")
+    d = {"t_ms": np.empty(n, np.uint32), **{k: np.empty(n, np.float32) for k in f32}, "of_q": np.empty(n, np.uint8),
+         "of_rate_x": np.empty(n, np.float32), "of_rate_y": np.empty(n, np.float32), "tof4": np.empty((n, 4), np.float32)}
+    order = ("t_ms",) + f32 + ("of_q", "of_rate_x", "of_rate_y", "tof4")
+    got = L.uqs_navlog_read(path.encode(), n, *(_ptr(d[k]) for k in order))
+    if got != n:
+        raise UqsError(ERR_BAD_ARG, f"nav log {path} changed while reading ({got} != {n})")
+    return d
 
 
 def scanlog_read(path: str, keep_nan_pose: bool = False) -> dict:

@@ -114,3 +114,58 @@ def test_n4_scanlog_reader(pkg, tmp_path):
         pkg.scanlog_read(bad)
     with pytest.raises(pkg.UqsError):
         pkg.scanlog_read(str(tmp_path / "missing.bin"))
+
+
+NAVLOG_HEADER = ("t_ms,state,want_arm,armed,mode,yaw_deg,alt_m,alt_src,x_m,y_m,vx_mps,vy_mps,"
+                 "rf_m,of_q,of_rate_x,of_rate_y,tof_f,tof_r,tof_b,tof_l,batt_v,batt_cells\n")
+
+
+def navlog_row(r):
+    """One row exactly as log_tick formats it (uav_local_nav.c:1586-1625): %.3f / %.4f fields, "nan" when missing."""
+    f3 = lambda v: "nan" if v is None else "%.3f" % v
+    s = "%d,%s,%d,%d,%d," % (r["t"], r["state"], 1, 1, 4)
+    s += f3(r["yaw"]) + "," + f3(r["alt"]) + ",RF,"
+    s += ("%.3f,%.3f,%.3f,%.3f," % (r["x"], r["y"], r["vx"], r["vy"])) if r["x"] is not None else "nan,nan,nan,nan,"
+    s += f3(r["rf"]) + "," + "%d," % r["q"]
+    s += ("%.4f,%.4f," % (r["ofx"], r["ofy"])) if r["ofx"] is not None else "nan,nan,"
+    s += "%.3f,%.3f,%.3f,%.3f," % tuple(r["tof"])
+    s += "%.3f,%d\n" % (11.1, 3)
+    return s
+
+
+def test_n4_navlog_reader(pkg, tmp_path):
+    """navlog.csv -> the SoA columns P0 consumes; 'nan' fields, appended flights, a second header, a truncated tail."""
+    rng = np.random.default_rng(12)
+    rows = []
+    for i in range(73):
+        rows.append({"t": 5_000_000_000 + 100 * i, "state": "HOVER" if i % 3 else "TURN", "yaw": float(rng.uniform(-180, 180)),
+                     "alt": 0.5 + 0.001 * i, "x": float(rng.uniform(-5, 5)), "y": float(rng.uniform(-5, 5)),
+                     "vx": float(rng.uniform(-1, 1)), "vy": float(rng.uniform(-1, 1)), "rf": 0.48, "q": int(rng.integers(0, 256)),
+                     "ofx": float(rng.uniform(-2, 2)), "ofy": float(rng.uniform(-2, 2)), "tof": rng.uniform(0.1, 4.0, 4).tolist()})
+    rows[4]["yaw"] = None                       # no attitude yet (:1596-1597)
+    rows[5]["x"] = None                         # no local position (:1603-1605)
+    rows[6]["ofx"] = None; rows[6]["q"] = 0     # stale optical flow (:1611-1616)
+    rows[7]["rf"] = None                        # stale rangefinder (:1607-1609)
+    path = str(tmp_path / "navlog.csv")
+    with open(path, "w") as f:
+        f.write(NAVLOG_HEADER)
+        for i, r in enumerate(rows):
+            if i == 40:
+                f.write(NAVLOG_HEADER)          # a log started in a fresh file and concatenated by hand
+            f.write(navlog_row(r))
+        f.write(navlog_row(rows[0])[:37])       # power cut mid-row: no newline, too few columns
+    d = pkg.navlog_read(path)
+    assert d["t_ms"].size == 73
+    f32 = lambda key: np.array([np.float32("nan") if r[key] is None else np.float32(float("%.3f" % r[key])) for r in rows], np.float32)
+    assert np.array_equal(d["t_ms"], np.array([r["t"] & 0xFFFFFFFF for r in rows], np.uint32))
+    for key, col in (("yaw", "yaw_deg"), ("alt", "alt_m"), ("x", "x_m"), ("rf", "rf_m")):
+        assert np.array_equal(d[col], f32(key), equal_nan=True), col
+    assert np.isnan(d["y_m"][5]) and np.isnan(d["vx_mps"][5]) and np.isnan(d["of_rate_y"][6])
+    want_ofx = np.array([np.float32("nan") if r["ofx"] is None else np.float32(float("%.4f" % r["ofx"])) for r in rows], np.float32)
+    assert np.array_equal(d["of_rate_x"], want_ofx, equal_nan=True)
+    assert np.array_equal(d["of_q"], np.array([r["q"] for r in rows], np.uint8))
+    assert np.array_equal(d["tof4"], np.array([[np.float32(float("%.3f" % v)) for v in r["tof"]] for r in rows], np.float32))
+    # the columns feed P0 as they are: t differences survive the 32-bit truncation
+    assert np.all(np.diff(d["t_ms"].astype(np.int64)) % (1 << 32) == 100)
+    with pytest.raises(pkg.UqsError):
+        pkg.navlog_read(str(tmp_path / "missing.csv"))
