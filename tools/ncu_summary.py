@@ -1,7 +1,11 @@
-"""Summarise an .ncu-rep: headline raw metrics + hot SASS regions (needs ncu on PATH; no GPU)."""
+"""Summarise an .ncu-rep: headline raw metrics + hot SASS regions (needs ncu on PATH; no GPU).
+usage: ncu_summary.py <report.ncu-rep> [full] [kernel=<regex>]   (kernel= restricts a multi-kernel report to one kernel)"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = [a.split("=", 1)[1] for a in sys.argv[2:] if a.startswith("kernel=")]
+sys.argv = [a for a in sys.argv if not a.startswith("kernel=")]
+kflt = ["-k", "regex:" + ksel[0]] if ksel else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + kflt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 keys = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed",
@@ -17,12 +21,15 @@ for r in rows[2:]:
     for h, u, v in zip(hdr, units, r):
         if h in keys or h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio"):
             print(f"  {h} [{u}] = {v}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + kflt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 hdr = rows[hi]
 isrc, ie, it, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Avg. Predicated-On Threads Executed"), hdr.index("# Samples")
 data = [r for r in rows[hi + 1:] if len(r) > ie and r[ie].isdigit()]
+half = len(data) // 2
+if half and len(data) % 2 == 0 and [r[isrc] + r[ie] for r in data[:half]] == [r[isrc] + r[ie] for r in data[half:]]:
+    data = data[:half]          # a report holding two launches lists the module's source once per launch
 tot = sum(int(r[ie]) for r in data) or 1
 tots = sum(int(r[isamp]) for r in data) or 1
 print(f"== SASS regions (total warp-instructions {tot}, samples {tots})")
