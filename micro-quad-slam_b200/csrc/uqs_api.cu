@@ -271,25 +271,45 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       const int bw = std::max(dims[0], 4), bh = std::max(dims[1], 1);
       int fpitch = (bw + 3) & ~3;
       if (((fpitch >> 2) & 1) == 0) fpitch += 4;
-      int ring_size = 256;                                  // per-warp collision table (power of two)
       const size_t region = (size_t)fpitch * bh;
-      const size_t dec_bytes = (size_t)nw * kDecSlotBytes + 16;      // ring of decoded frames (+ alignment)
-      while (ring_size > 32 && region + (size_t)(ring_size + 4) * nw + dec_bytes > kFlightSmemMax) ring_size >>= 1;
-      const size_t fsmem = region + (size_t)(ring_size + 4) * nw + dec_bytes;     // + one scratch word per warp
-      int f_ctas = 0;
-      if (fsmem <= kFlightSmemMax) {
-        e = flights_prepare(nw, fsmem, &f_ctas);
-        if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights attributes");
+      // Warps per resident CTA.  Measured over box sizes from 30 KB (7 CTAs per SM) to 173 KB (one): the kernel wants
+      // >= 16 resident warps per SM from as few warps per CTA as possible (per-frame work is paid per warp), and never
+      // more than 16 per CTA (a frame has ~80-400 steps to share out).  Few flights: more warps per CTA (nw_min).
+      int ring_size = 256, f_ctas = 0, fnw = nw;
+      size_t fsmem = 0;
+      auto fit = [&](int w, int* ring, size_t* bytes, int* ctas) -> cudaError_t {
+        *ring = 256;                                        // per-warp collision table (power of two)
+        const size_t dec_bytes = (size_t)w * kDecSlotBytes + 16;      // ring of decoded frames (+ alignment)
+        while (*ring > 32 && region + (size_t)(*ring + 4) * w + dec_bytes > kFlightSmemMax) *ring >>= 1;
+        *bytes = region + (size_t)(*ring + 4) * w + dec_bytes;         // + one scratch word per warp
+        *ctas = 0;
+        return *bytes <= kFlightSmemMax ? flights_prepare(w, *bytes, ctas) : cudaSuccess;
+      };
+      if (g_ctx.flight_warps) {
+        e = fit(fnw, &ring_size, &fsmem, &f_ctas);
+      } else {
+        e = cudaSuccess;
+        for (int w : { 4, 8, 16 }) {
+          if (w < nw) continue;                             // nw: the minimum the flight count asks for
+          int r, c;
+          size_t bts;
+          if ((e = fit(w, &r, &bts, &c)) != cudaSuccess) break;
+          if (c < 1) break;                                 // more warps only need more shared memory
+          fnw = w; ring_size = r; fsmem = bts; f_ctas = c;
+          if (c * w >= 16) break;
+        }
       }
+      if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights attributes");
       if (g_ctx.engine == 2 && f_ctas < 1) {
         set_error("engine 2: the touched region %dx%d of a flight does not fit %zu B of shared memory", bw, bh, kFlightSmemMax);
         return UQS_ERR_BAD_ARG;
       }
-      // auto: resident when several CTAs fit an SM (barrier stalls of one hide behind the others) and there is at
-      // least a flight per SM (measured crossover); otherwise the sub-tile engine (time-sliced when flights are few)
+      // auto: resident when the box fits and there is at least a flight per SM (measured crossover; with one CTA of
+      // 16 warps per SM it still beats the sub-tile engine by 1.6x on the 668^2 and 800^2 grids of config 5);
+      // otherwise the sub-tile engine (time-sliced when flights are few)
       // (a chunk of the host-buffer pipeline shares the chip with its neighbours: no flight-count condition there)
       const bool pipelined = g_ctx.w != &g_ctx.works[0];
-      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || (f_ctas >= 2 && (nf >= g_ctx.sm_count || pipelined)));
+      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || nf >= g_ctx.sm_count || pipelined);
       if (resident) {
         FlightArgs FA;
         FA.frames = (const uint4*)g_ctx.w->frames.p;
@@ -308,7 +328,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         if (e != cudaSuccess) return cuda_fail(e, "memset before k_replay_flights");
         const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)f_ctas * g_ctx.sm_count);
         KernelTimer t_rep(2);
-        e = flights_launch(nw, fgrid, fsmem, st, FA);
+        e = flights_launch(fnw, fgrid, fsmem, st, FA);
         t_rep.stop();
         if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights launch");
         g_ctx.launches += 2;
