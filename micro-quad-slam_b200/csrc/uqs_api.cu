@@ -192,11 +192,11 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   int pitch = (sw + 3) & ~3;
   if (((pitch >> 2) & 1) == 0) pitch += 4;            // odd word pitch: column walks hit 32 banks
   const int pitch_cells = sw | 1;
-  if (slices > 1 && g_ctx.tune_slices == 0 && (size_t)pitch_cells * sh * 4 * kReplayWarps > 227u * 1024u)
+  if (slices > 1 && g_ctx.tune_slices == 0 && ((size_t)pitch_cells * sh * 4 + kReplayQueueBytes) * kReplayWarps > 227u * 1024u)
     slices = 1;                                        // a forced large sub-tile leaves no room for 32-bit map cells
   const int gps = (gpf + slices - 1) / slices;          // 32-frame groups per slice
   const int tile_bytes = slices > 1 ? std::max(pitch * sh, pitch_cells * sh * 4) : pitch * sh;
-  size_t smem = (size_t)tile_bytes * kReplayWarps;
+  size_t smem = (size_t)tile_bytes * kReplayWarps + (size_t)kReplayQueueBytes * kReplayWarps;   // tiles + candidate queues
 
   // Engine 2 keeps, per CTA, the bounding box of the cells one flight can touch resident in shared memory
   // (frame-synchronous).  Whether it fits -- and how many CTAs share an SM -- is only known

@@ -508,14 +508,22 @@ __device__ __forceinline__ int div_small(int num, int den) {
   return q;
 }
 
-// Apply, in beam order, the part of every ray of one frame that lies inside the warp's
+// Candidate queue of a warp (shared memory, 64 entries, circular): rays whose bounding box meets the warp's
+// sub-tile, in (frame, beam) order.  Exact clipping costs ~100 instructions whether one beam of a frame meets the
+// sub-tile or all 32 do -- and on fine grids a sub-tile sees one to three beams of a frame -- so candidates of many
+// frames are collected first and clipped 32 at a time.
+constexpr int kQueueEntries = 64;
+constexpr int kQueueBytes = kQueueEntries * 12;          // w0 (dx,dy,flags), w1 (reciprocal), origin cell: three words each
+static_assert(kQueueBytes == kReplayQueueBytes, "the host sizes the queues");
+
+// Apply, in queue (= frame, beam) order, the part of `count` <= 32 queued rays that lies inside the warp's
 // sub-tile [X0,X1) x [Y0,Y1).
-//   1. lane b clips beam b EXACTLY: cell k of a ray is (major0 + k*s, minor0 + s'*q(k)) with
+//   1. lane i clips entry i EXACTLY: cell k of a ray is (major0 + k*s, minor0 + s'*q(k)) with
 //      q(k) = floor((k*n + m/2)/m) non-decreasing, so "inside the tile" is one interval
 //      [ka, kb] of k: the major axis gives it directly, the minor axis by inverting q:
 //        q(k) >= a  <=>  k >= ceil((a*m - m/2)/n),   q(k) <= b  <=>  k <= floor(((b+1)*m - m/2 - 1)/n)
-//      and packs what the cell loop needs into four words;
-//   2. the warp walks the surviving beams in order, lanes along the ray: the cells of one ray
+//      and packs what the cell loop needs into five words;
+//   2. the warp walks the surviving rays in order, lanes along the ray: the cells of one ray
 //      are distinct, so plain byte read-modify-writes are race-free and in reference order.
 //
 // MAP = false: the tile holds int8 log-odds values (the log, or its first time slice, from a known start).
@@ -526,17 +534,16 @@ __device__ __forceinline__ int div_small(int num, int den) {
 //   outside +-(lo_max-lo_min)) only matters while f(lo_min) < f(lo_max), and then it never saturated
 //   ("time slices").  k_compose_slices applies the maps in slice order.
 template <bool MAP>
-__device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, int lane, int gx0,
-                                            int gy0, uint2 rec, int X0, int X1, int Y0, int Y1) {
-  uint32_t p1, p2, p3;      // n2 | m<<16 ; cK | cQ<<16 ; ka | kb<<11 | hit<<22
+__device__ __forceinline__ void apply_queued(const TileConsts& A, uint32_t tile, int lane, uint32_t queue, int head,
+                                             int count, int X0, int X1, int Y0, int Y1) {
+  uint32_t p1, p2, p3, p4, inv_l;      // n2 | m<<16 ; cK | cQ<<16 ; ka | kb<<11 | hit<<22 ; origin address ; reciprocal
   bool live;
   {
-    const int dx = sext12(rec.x), dy = sext12(rec.x >> 12);
-    // cheap reject first: a frame's box covers the whole fan, most sub-tiles inside it see no beam at all
-    const int ex = gx0 + dx, ey = gy0 + dy;
-    const bool near = (rec.x & kRayValid) != 0u && min(gx0, ex) < X1 && max(gx0, ex) >= X0 && min(gy0, ey) < Y1 &&
-                      max(gy0, ey) >= Y0;
-    if (!__any_sync(0xffffffffu, near)) return;
+    const uint32_t at = queue + 4u * (uint32_t)((head + lane) & (kQueueEntries - 1));
+    const uint32_t w0 = lds_u32(at), org = lds_u32(at + 8u * kQueueEntries);
+    inv_l = lds_u32(at + 4u * kQueueEntries);
+    const int gx0 = (int)(org & 0xffffu), gy0 = (int)(org >> 16);
+    const int dx = sext12(w0), dy = sext12(w0 >> 12);
     const int adx = abs(dx), ady = abs(dy);
     const bool xmaj = adx >= ady;
     const int m = xmaj ? adx : ady, n = xmaj ? ady : adx, h = m >> 1;
@@ -548,7 +555,7 @@ __device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, 
     int kb = min(majpos ? (A1 - 1 - c0) : (c0 - A0), m);
     const int qlo = minpos ? (B0 - c1) : (c1 - (B1 - 1));
     const int qhi = minpos ? (B1 - 1 - c1) : (c1 - B0);
-    live = (rec.x & kRayValid) != 0u && qhi >= 0 && qlo <= n;
+    live = lane < count && qhi >= 0 && qlo <= n;
     if (qlo > 0 && qlo <= n) {                                   // n >= 1 here
       const int num = qlo * m - h;                               // > 0 because qlo*m >= m > h
       ka = max(ka, div_small(num + n - 1, n));
@@ -560,17 +567,18 @@ __device__ __forceinline__ void apply_frame(const TileConsts& A, uint32_t tile, 
     const int cQ = minpos ? (xmaj ? pitch : 1) : (xmaj ? -pitch : -1);
     p1 = (uint32_t)(2 * n) | ((uint32_t)m << 16);
     p2 = ((uint32_t)cK & 0xffffu) | ((uint32_t)cQ << 16);
-    p3 = (uint32_t)ka | ((uint32_t)kb << 11) | ((rec.x & kRayHit) ? (1u << 22) : 0u);
+    p3 = (uint32_t)ka | ((uint32_t)kb << 11) | ((w0 & kRayHit) ? (1u << 22) : 0u);
+    p4 = tile + ((uint32_t)((gy0 - Y0) * pitch + (gx0 - X0)) << (MAP ? 2 : 0));
   }
   unsigned active = __ballot_sync(0xffffffffu, live);
-  const uint32_t base = tile + ((uint32_t)((gy0 - Y0) * A.pitch + (gx0 - X0)) << (MAP ? 2 : 0));
   while (active) {
     const int b = __ffs(active) - 1;
     active &= active - 1;
-    const uint32_t inv = __shfl_sync(0xffffffffu, rec.y, b);
+    const uint32_t inv = __shfl_sync(0xffffffffu, inv_l, b);
     const uint32_t q1 = __shfl_sync(0xffffffffu, p1, b);
     const uint32_t q2 = __shfl_sync(0xffffffffu, p2, b);
     const uint32_t q3 = __shfl_sync(0xffffffffu, p3, b);
+    const uint32_t base = __shfl_sync(0xffffffffu, p4, b);
     const int n2 = (int)(q1 & 0xffffu), m = (int)(q1 >> 16), h2 = m & ~1;
     const int cK = (int)(short)(q2 & 0xffffu), cQ = (int)q2 >> 16;
     const int k1 = (int)((q3 >> 11) & 0x7ffu);
@@ -604,6 +612,8 @@ k_replay_tiles(ReplayArgs A) {
   const int wic = threadIdx.x >> 5;
   int8_t* tile = reinterpret_cast<int8_t*>(uqs_smem) + (size_t)wic * A.tile_bytes;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  // the warp's candidate queue sits behind the CTA's tiles
+  const uint32_t queue_s = (uint32_t)__cvta_generic_to_shared(uqs_smem) + (uint32_t)(kReplayWarps * A.tile_bytes + wic * kQueueBytes);
   const int lo_free = in_reg(A.lo_free), lo_occ = in_reg(A.lo_occ), lo_min = in_reg(A.lo_min), lo_max = in_reg(A.lo_max);
   const TileConsts CV = { in_reg(A.pitch), lo_free, lo_occ, lo_min, lo_max, in_reg(A.end_nohit) };     // value tiles
   const TileConsts CM = { in_reg(A.pitch_cells), lo_free, lo_occ, lo_min, lo_max, CV.end_nohit };       // map tiles
@@ -656,12 +666,22 @@ k_replay_tiles(ReplayArgs A) {
     }
     __syncwarp();
 
-    // ---- walk the slice's frames in order, culling by group and frame bounding boxes ------
+    // ---- walk the slice's frames in order, culling by group and frame bounding boxes; rays whose own
+    // bounding box meets the sub-tile are queued and applied 32 at a time (apply_queued) ------------------
     const uint2* groups = A.groups + (size_t)flight * A.groups_per_flight;
     const uint4* frames = A.frames + (size_t)flight * A.n_frames;
     const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
     const int g_begin = slice * A.groups_per_slice;
     const int g_end = min(g_begin + A.groups_per_slice, A.groups_per_flight);
+    int qhead = 0, qn = 0;
+    auto flush = [&]() {
+      const int count = min(qn, 32);
+      __syncwarp();
+      if (map) apply_queued<true>(CM, tile_s, lane, queue_s, qhead, count, X0, X1, Y0, Y1);
+      else     apply_queued<false>(CV, tile_s, lane, queue_s, qhead, count, X0, X1, Y0, Y1);
+      qhead = (qhead + count) & (kQueueEntries - 1);
+      qn -= count;
+    };
     for (int g0 = g_begin; g0 < g_end; g0 += 32) {
       bool ghit = false;
       if (g0 + lane < g_end) {
@@ -676,7 +696,7 @@ k_replay_tiles(ReplayArgs A) {
         uint4 fr = make_uint4(0, 0, kEmptyBoxLoHi, kEmptyBoxLoHi);
         if (f0 + lane < A.n_frames) fr = __ldg(&frames[f0 + lane]);
         unsigned fmask = __ballot_sync(0xffffffffu, box_overlaps(fr.z, fr.w, X0, X1, Y0, Y1));
-        // software pipeline: the next hit frame's ray records are in flight while this one is applied
+        // software pipeline: the next hit frame's ray records are in flight while this one is tested
         uint2 rec_next = make_uint2(0, 0);
         if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
         while (fmask) {
@@ -686,11 +706,23 @@ k_replay_tiles(ReplayArgs A) {
           if (fmask) rec_next = __ldg(&rays[(size_t)(f0 + __ffs(fmask) - 1) * 32 + lane]);
           const int gx0 = (int)(__shfl_sync(0xffffffffu, fr.x, fi) & 0xffffu);
           const int gy0 = (int)(__shfl_sync(0xffffffffu, fr.y, fi) & 0xffffu);
-          if (map) apply_frame<true>(CM, tile_s, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
-          else     apply_frame<false>(CV, tile_s, lane, gx0, gy0, rec, X0, X1, Y0, Y1);
+          const int ex = gx0 + sext12(rec.x), ey = gy0 + sext12(rec.x >> 12);
+          const bool near = (rec.x & kRayValid) != 0u && min(gx0, ex) < X1 && max(gx0, ex) >= X0 && min(gy0, ey) < Y1 &&
+                            max(gy0, ey) >= Y0;
+          const unsigned nm = __ballot_sync(0xffffffffu, near);
+          if (nm == 0u) continue;
+          if (near) {
+            const uint32_t at = queue_s + 4u * (uint32_t)((qhead + qn + __popc(nm & ((1u << lane) - 1u))) & (kQueueEntries - 1));
+            sts_u32(at, rec.x);
+            sts_u32(at + 4u * kQueueEntries, rec.y);
+            sts_u32(at + 8u * kQueueEntries, (uint32_t)gx0 | ((uint32_t)gy0 << 16));
+          }
+          qn += __popc(nm);
+          if (qn >= 32) flush();                               // at most 63 queued before, at most 31 after
         }
       }
     }
+    while (qn > 0) flush();
     __syncwarp();
 
     // ---- write the sub-tile back: values into the grid, maps into the slice scratch ---------

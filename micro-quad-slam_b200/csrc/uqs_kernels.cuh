@@ -6,6 +6,7 @@ namespace uqs {
 
 constexpr int kReplayThreads = 256;               // 8 warps per CTA, each owning one sub-tile
 constexpr int kReplayWarps = kReplayThreads / 32;
+constexpr int kReplayQueueBytes = 64 * 12;         // per-warp candidate queue of k_replay_tiles (kQueueBytes)
 constexpr int kDecSlotBytes = 32 * 16 + 16;       // one decoded frame in the resident engine's ring
 constexpr int kJobGroup = 64;                     // flights per scheduling group of the sub-tile engine
 
