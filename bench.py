@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--cpu-flights-per-core", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the single-flight configs (c1, c2) reported for information")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 sub-tiles, 2 resident (tuning experiments)")
     ap.add_argument("--flight-warps", type=int, default=0, help="warps per resident CTA (0 = library default)")
     args = ap.parse_args()
@@ -414,11 +415,36 @@ def main():
         cpu = {"value": ups, "unit": "updates/s", "cores": used, "kind": kind, "frames_per_s": fps,
                "sample": f"{n} of {F} flights ({fpc} per worker process), P0 + mapping, logs in RAM, {wall:.2f} s wall"}
 
+    # ---- the single-flight BASELINE configurations, device-resident (information only; parity: tests/test_gpu_fullsize.py) ----
+    others = []
+    if world == 1 and args.workload == "c3" and not args.flights and not args.no_other_configs:
+        for name in ("c1", "c2"):
+            wo = synth.CONFIGS[name]
+            do = synth.generate(wo)
+            po = wo.params()
+            xo, yo = synth.frame_poses(do, do["x_true"], do["y_true"])
+            to = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (xo, yo, do["frame_yaw_deg"], do["ranges"])]
+            go = torch.empty((wo.n_flights, po.H, po.W), dtype=torch.int8, device=dev)
+            so = m.replay_dev(po, wo.n_flights, wo.n_frames, *(a.data_ptr() for a in to), go.data_ptr(), want_stats=True)
+            for _ in range(2):
+                m.replay_dev(po, wo.n_flights, wo.n_frames, *(a.data_ptr() for a in to), go.data_ptr())
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                m.replay_dev(po, wo.n_flights, wo.n_frames, *(a.data_ptr() for a in to), go.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            t_ms = e0.elapsed_time(e1) / args.steps
+            others.append({"workload": f"BASELINE config {wo.config_id}: {wo.name}", "frames": wo.n_frames, "grid": f"{po.W}x{po.H}",
+                           "ms_per_replay": t_ms, "updates_per_s": so["ray_cell_updates"] / (t_ms * 1e-3),
+                           "frames_per_s": wo.n_frames / (t_ms * 1e-3), "what": "ray set-up + replay from poses in HBM"})
+
     out = {"metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8",
            "data": "synthetic", "config": describe(w, world), "frames_per_s": F * NF * world / (ms_per_step * 1e-3),
            "ray_cell_updates_per_step": total_updates, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-           "gpu_launches": int(launches), "clocks": clk, "host": {"cpus": os.cpu_count(), "rank_local_cpus": local_cpus}}
+           "gpu_launches": int(launches), "clocks": clk, "host": {"cpus": os.cpu_count(), "rank_local_cpus": local_cpus},
+           "other_configs": others}
     out_fd.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
