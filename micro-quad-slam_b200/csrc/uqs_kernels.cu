@@ -917,7 +917,9 @@ k_replay_flights(FlightArgs A) {
       const int kshared = min(B.k0, mmax + 1);
 
       // ---- steps k < K0: beams may meet in a cell; detect and keep beam order --------------------
-      for (int k = w; k < kshared; k += NW) {
+      // the warp whose turn it is to decode a frame (w == f mod NW) gets the last of the collision steps, the others
+      // the first ones: with K0 ~ 7 and four warps that is 1 step for the decoder and 2 for everyone else
+      for (int k = (w - f - 1) & (NW - 1); k < kshared; k += NW) {
         const bool act = k <= m;
         const int q = minor_steps(k, n2, h2, inv);
         const int addr = base + k * sM + q * sN;
