@@ -272,14 +272,14 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       int fpitch = (bw + 3) & ~3;
       if (((fpitch >> 2) & 1) == 0) fpitch += 4;
       const size_t region = (size_t)fpitch * bh;
-      // Warps per resident CTA.  Measured over box sizes from 30 KB (7 CTAs per SM) to 173 KB (one): the kernel wants
-      // >= 16 resident warps per SM from as few warps per CTA as possible (per-frame work is paid per warp), and never
+      // Warps per resident CTA.  Measured over box sizes from 17 KB (8 CTAs per SM) to 173 KB (one): the kernel wants
+      // >= 24 resident warps per SM from as few warps per CTA as possible (per-frame work is paid per warp), and never
       // more than 16 per CTA (a frame has ~80-400 steps to share out).  Few flights: more warps per CTA (nw_min).
       int ring_size = 256, f_ctas = 0, fnw = nw;
       size_t fsmem = 0;
       auto fit = [&](int w, int* ring, size_t* bytes, int* ctas) -> cudaError_t {
         *ring = 256;                                        // per-warp collision table (power of two)
-        const size_t dec_bytes = (size_t)w * kDecSlotBytes + 16;      // ring of decoded frames (+ alignment)
+        const size_t dec_bytes = (size_t)std::min(w, kDecSlotsMax) * kDecSlotBytes + 16;      // ring of decoded frames (+ alignment)
         while (*ring > 32 && region + (size_t)(*ring + 4) * w + dec_bytes > kFlightSmemMax) *ring >>= 1;
         *bytes = region + (size_t)(*ring + 4) * w + dec_bytes;         // + one scratch word per warp
         *ctas = 0;
@@ -296,7 +296,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
           if ((e = fit(w, &r, &bts, &c)) != cudaSuccess) break;
           if (c < 1) break;                                 // more warps only need more shared memory
           fnw = w; ring_size = r; fsmem = bts; f_ctas = c;
-          if (c * w >= 16) break;
+          if (c * w >= 24) break;
         }
       }
       if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights attributes");

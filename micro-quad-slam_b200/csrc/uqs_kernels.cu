@@ -877,18 +877,19 @@ k_replay_flights(FlightArgs A) {
 
     const uint4* frames = A.frames + (size_t)flight * A.n_frames;
     const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
-    // Beam decode is shared: warp (f mod NW) decodes frame f + NW/2 into a ring of NW slots in shared memory
-    // (32 lanes x 16 B + one frame word per slot); every warp then reads its lane's 16 B per frame.  A warp
+    // Beam decode is shared: warp (f mod NW) decodes frame f + L into a ring of R = min(NW, 4) slots in shared memory
+    // (32 lanes x 2 x 16 B + one frame record per slot); every warp then reads its lane's 32 B per frame.  A warp
     // therefore decodes -- and loads raw records for -- only every NW-th frame, one turn ahead.
-    constexpr int L = NW / 2;
+    constexpr int R = NW < kDecSlotsMax ? NW : kDecSlotsMax;      // slots of the ring (frame g lives in slot g mod R)
+    constexpr int L = R / 2;                                       // frames of decode lead
     auto decode_store = [&](uint2 rec, uint2 org, int slot) {
       const Beam b = decode_beam(rec, org, P, bx0, by0, A.lo_occ, A.end_nohit);
       const int mx = __reduce_max_sync(0xffffffffu, b.m);
       const uint32_t at = dec_sa + (uint32_t)slot * kDecSlotBytes;
-      sts_v4(at + 16u * (uint32_t)lane, b.inv, (uint32_t)b.n2 | ((uint32_t)(b.m + 1) << 16),
-             ((uint32_t)b.sM & 0xffffu) | ((uint32_t)b.sN << 16),
-             ((uint32_t)b.end_delta & 0xffu) | ((uint32_t)b.ra << 8) | (b.rb < 0 ? 0x1000u : 0u));
-      if (lane == 0) sts_v4(at + 512u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, (org.y & kFrameSorted) ? 1u : 0u);
+      // two 16-byte records per beam, stored as the registers the step loops use (no unpacking by the NW readers)
+      sts_v4(at + 16u * (uint32_t)lane, b.inv, (uint32_t)b.n2, (uint32_t)b.m, (uint32_t)b.sM);
+      sts_v4(at + 512u + 16u * (uint32_t)lane, (uint32_t)b.sN, (uint32_t)b.end_delta, (uint32_t)b.ra, (uint32_t)b.rb);
+      if (lane == 0) sts_v4(at + 1024u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, (org.y & kFrameSorted) ? 1u : 0u);
     };
     if (w < L && w < A.n_frames)
       decode_store(__ldg(&rays[(size_t)w * 32 + lane]), __ldg(reinterpret_cast<const uint2*>(&frames[w])), w);
@@ -901,20 +902,20 @@ k_replay_flights(FlightArgs A) {
     }
     __syncthreads();
     for (int f = 0; f < A.n_frames; f++) {
-      const uint32_t at = dec_sa + (uint32_t)(f & (NW - 1)) * kDecSlotBytes;
-      const uint4 dv = lds_v4(at + 16u * (uint32_t)lane);
-      const uint4 fv = lds_v4(at + 512u);
+      const uint32_t at = dec_sa + (uint32_t)(f & (R - 1)) * kDecSlotBytes;
+      const uint4 dv = lds_v4(at + 16u * (uint32_t)lane), dw = lds_v4(at + 512u + 16u * (uint32_t)lane);
+      const uint4 fv = lds_v4(at + 1024u);
       const uint32_t inv = dv.x;
-      const int n2 = (int)(dv.y & 0xffffu), m = (int)(dv.y >> 16) - 1, h2 = m & ~1;
-      const int sM = (int)(short)(dv.z & 0xffffu), sN = (int)dv.z >> 16;
+      const int n2 = (int)dv.y, m = (int)dv.z, h2 = m & ~1;
+      const int sM = (int)dv.w, sN = (int)dw.x;
       Beam B;
-      B.end_delta = (int)(signed char)(dv.w & 0xffu);
-      B.ra = (int)((dv.w >> 8) & 0xfu);
-      B.rb = (dv.w & 0x1000u) ? -1 : 1;
+      B.end_delta = (int)dw.y;
+      B.ra = (int)dw.z;
+      B.rb = (int)dw.w;
       B.k0 = (int)fv.y;
       const int base = (int)fv.x, mmax = (int)fv.z;
       const bool sorted = fv.w != 0u;
-      const int kshared = min(B.k0, mmax + 1);
+      const int kshared = B.k0;                      // k_ray_setup caps K0 at mmax + 1
 
       // ---- steps k < K0: beams may meet in a cell; detect and keep beam order --------------------
       // the warp whose turn it is to decode a frame (w == f mod NW) gets the last of the collision steps, the others
@@ -1003,7 +1004,7 @@ k_replay_flights(FlightArgs A) {
 
       // ---- steps k >= K0: every cell is touched by one beam only; four steps in flight, branch-free
       // (lanes past their beam's end read-modify-write a scratch byte behind the resident region)
-      int k = w + ((max(B.k0 - w, 0) + NW - 1) / NW) * NW;
+      int k = B.k0 + ((w - B.k0) & (NW - 1));          // first step >= K0 of this warp's residue class
       const uint32_t gbase = grid_sa + (uint32_t)base;
       const int free_delta = -lo_free;
       constexpr int UN = UQS_UN;                    // steps in flight per warp
@@ -1038,7 +1039,7 @@ k_replay_flights(FlightArgs A) {
       }
       if ((f & (NW - 1)) == w) {                    // this warp's turn: decode frame f + L, prefetch its next turn
         const int g = f + L;
-        if (g < A.n_frames) decode_store(raw_rec, raw_org, g & (NW - 1));
+        if (g < A.n_frames) decode_store(raw_rec, raw_org, g & (R - 1));
         const int gn = min(g + NW, A.n_frames - 1);
         raw_rec = __ldg(&rays[(size_t)gn * 32 + lane]);
         raw_org = __ldg(reinterpret_cast<const uint2*>(&frames[gn]));

@@ -7,7 +7,8 @@ namespace uqs {
 constexpr int kReplayThreads = 256;               // 8 warps per CTA, each owning one sub-tile
 constexpr int kReplayWarps = kReplayThreads / 32;
 constexpr int kReplayQueueBytes = 64 * 12;         // per-warp candidate queue of k_replay_tiles (kQueueBytes)
-constexpr int kDecSlotBytes = 32 * 16 + 16;       // one decoded frame in the resident engine's ring
+constexpr int kDecSlotBytes = 32 * 32 + 16;       // one decoded frame in the resident engine's ring
+constexpr int kDecSlotsMax = 4;                    // the ring holds min(warps per CTA, 4) frames
 constexpr int kJobGroup = 64;                     // flights per scheduling group of the sub-tile engine
 
 struct ReplayArgs {

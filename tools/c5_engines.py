@@ -12,7 +12,7 @@ for ir in [int(a) for a in sys.argv[1:]] or [1, 2]:
     t = [torch.from_numpy(np.ascontiguousarray(cat(k))).to(dev) for k in ("x_true", "y_true", "frame_yaw_deg", "ranges")]
     g = torch.empty((F, p.H, p.W), dtype=torch.int8, device=dev)
     ref = None
-    for eng, nw in [(0, 0), (2, 4), (2, 8), (2, 16)]:
+    for eng, nw in [(0, 0), (2, 4), (2, 8), (2, 16), (2, 32)]:
         m.set_engine(eng, nw)
         try:
             st = m.replay_dev(p, F, N, *(a.data_ptr() for a in t), g.data_ptr(), want_stats=True)
