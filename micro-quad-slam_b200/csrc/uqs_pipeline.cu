@@ -77,22 +77,21 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   if (rc) return rc;
   const bool flow = L.t_ms != nullptr;
   const size_t cells = (size_t)p->W * p->H;
-  // Chunk schedule: body chunks of 4 flights per SM (one full wave of resident replay CTAs on the 400x400
-  // ensemble), after a short ramp up (1, 2 flights per SM: their H2D cannot hide behind any kernel) and before a
-  // short ramp down (2, 1: the last chunk's kernels and D2H hide behind nothing).
+  // Chunk schedule: chunks of 2 flights per SM between a first and a last chunk of 1 per SM (the first chunk's H2D and
+  // the last chunk's kernels and D2H hide behind nothing).  The copies, not the kernels, bound this pipeline on the
+  // 400x400 ensemble (1.83 GB in at ~51 GB/s while grids flow out), so small chunks -- a short tail after the last
+  // byte has arrived -- win: measured 39.8 ms at 2 per SM, 42 ms at 3, 43 ms at 4.
   std::vector<int> starts;                      // flight index where chunk c begins; starts.back() = n_flights
   {
     const int sm = g_ctx.sm_count;
-    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 4 * sm;
+    int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 2 * sm;
     const size_t stage_budget = (size_t)6 << 30;                          // bound the staging buffers (kStages x chunk)
     if ((size_t)chunk_cap * n_frames * 152 * kStages > stage_budget)
       chunk_cap = std::max<int>(1, (int)(stage_budget / ((size_t)n_frames * 152 * kStages)));
-    if (g_ctx.host_chunk == 0 && chunk_cap == 4 * sm && n_flights >= 12 * sm) {
-      int f = 0;
-      for (int c : { sm, 2 * sm }) { starts.push_back(f); f += c; }
-      const int body = n_flights - f - 3 * sm, n_mid = (body + chunk_cap - 1) / chunk_cap;
-      for (int i = 0; i < n_mid; i++) starts.push_back(f + (int)((long long)body * i / n_mid));
-      starts.push_back(n_flights - 3 * sm);
+    if (g_ctx.host_chunk == 0 && chunk_cap == 2 * sm && n_flights >= 8 * sm) {
+      starts.push_back(0);
+      const int body = n_flights - 2 * sm, n_mid = (body + chunk_cap - 1) / chunk_cap;
+      for (int i = 0; i < n_mid; i++) starts.push_back(sm + (int)((long long)body * i / n_mid));
       starts.push_back(n_flights - sm);
     } else {
       const int n_want = (n_flights + chunk_cap - 1) / chunk_cap;
