@@ -184,16 +184,21 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(w):
-    """dram bytes per replay launch from the committed ncu --set full capture, when it is for this workload."""
+def recorded_capture(w):
+    """Figures of the committed ncu --set full capture of the replay kernel, when it is for this workload."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         if t.get("workload") == w.name and t.get("flights") == w.n_flights and t.get("frames") == w.n_frames:
-            return t["dram_bytes_per_launch"]
+            return t
     except Exception:
         pass
-    return None
+    return {}
+
+
+def recorded_traffic(w):
+    """dram bytes per replay launch from that capture (None when it is for another workload)."""
+    return recorded_capture(w).get("dram_bytes_per_launch")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,11 +400,15 @@ def main():
     replay_ms = kms[2] / max(args.steps, 1)                           # summed over the step's replay launches
     achieved = b_alg / (replay_ms * 1e-3) / 1e9
     rmw_peak = m.measure_rmw_peak()
+    cap = recorded_capture(w)
     roofline = {"bound": "hbm", "kernel": "k_replay_tiles/k_replay_flights", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": recorded_traffic(w),
                 "algorithmic_bytes_per_step": int(b_alg), "kernel_ms_per_step": replay_ms,
                 "kernel_share_of_step": replay_ms / ms_per_step,
                 "setup_kernel_ms_per_step": kms[1] / args.steps, "pose_kernels_ms_per_step": kms[0] / args.steps,
+                "smem_pipe_recorded": {"pct_of_peak": cap.get("smem_pipe_pct_of_peak"), "issue_slots_pct": cap.get("issue_slots_pct_of_peak"),
+                                       "note": "shared-memory wavefronts of the replay kernel in the committed ncu capture "
+                                               "(profiles/r1_ncu_full_k_replay_flights_c3.txt): the pipe this kernel is bound by"},
                 "onchip_rmw": {"achieved_updates_per_s": U / (replay_ms * 1e-3), "peak_updates_per_s": rmw_peak,
                                "frac": U / (replay_ms * 1e-3) / rmw_peak,
                                "note": "peak = conflict-free shared-memory byte RMW microbenchmark on this GPU"}}
