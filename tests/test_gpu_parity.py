@@ -372,6 +372,38 @@ def test_host_pipeline_chunking_does_not_change_results(gpu, oracle, synth):
         gpu.set_host_chunk(0)
 
 
+def test_unaligned_range_log_takes_the_plain_load_path(gpu, oracle, synth):
+    """k_ray_setup stages a block's range readings with one TMA bulk copy, which needs a 16-byte aligned log; a
+    log that starts 4 bytes off must give the same grids through the plain-load path (both engines)."""
+    import torch
+    w = synth.scaled(synth.CONFIGS["c3"], n_flights=3, n_samples=333)
+    d = synth.generate(w)
+    p = w.params()
+    x, y = synth.frame_poses(d, d["x_true"], d["y_true"])
+    want, U = oracle_grids(oracle, p, d, x, y)
+    dev = torch.device("cuda:0")
+    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        tx, ty, tyaw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x, y, d["frame_yaw_deg"]))
+        flat = torch.from_numpy(np.ascontiguousarray(d["ranges"])).to(dev).reshape(-1)
+        for shift in (0, 1, 2, 3):                       # floats: 0 -> aligned (TMA), 1..3 -> 4/8/12 bytes off
+            buf = torch.empty(flat.numel() + 4, dtype=torch.float32, device=dev)
+            view = buf[shift:shift + flat.numel()]
+            view.copy_(flat)
+            assert (view.data_ptr() % 16 == 0) == (shift == 0)
+            for engine in (1, 2):
+                gpu.set_engine(engine, 0)
+                g = torch.zeros((w.n_flights, p.H, p.W), dtype=torch.int8, device=dev)
+                st = gpu.replay_dev(p, w.n_flights, w.n_frames, tx.data_ptr(), ty.data_ptr(), tyaw.data_ptr(), view.data_ptr(),
+                                    g.data_ptr(), want_stats=True)
+                got = g.cpu().numpy()
+                assert np.array_equal(got, want), (shift, engine, first_diff(got, want))
+                assert st["ray_cell_updates"] == U
+    finally:
+        gpu.set_engine(0, 0)
+        gpu.set_stream(None)
+
+
 # ----------------------------------------------------------------------------------------------
 # P0
 # ----------------------------------------------------------------------------------------------
