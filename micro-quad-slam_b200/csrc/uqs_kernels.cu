@@ -886,9 +886,11 @@ k_replay_flights(FlightArgs A) {
       const Beam b = decode_beam(rec, org, P, bx0, by0, A.lo_occ, A.end_nohit);
       const int mx = __reduce_max_sync(0xffffffffu, b.m);
       const uint32_t at = dec_sa + (uint32_t)slot * kDecSlotBytes;
-      // two 16-byte records per beam, stored as the registers the step loops use (no unpacking by the NW readers)
+      // 16 bytes per beam stored as the registers the free-space loop uses (no unpacking by the NW readers)
       sts_v4(at + 16u * (uint32_t)lane, b.inv, (uint32_t)b.n2, (uint32_t)b.m, (uint32_t)b.sM);
-      sts_v4(at + 512u + 16u * (uint32_t)lane, (uint32_t)b.sN, (uint32_t)b.end_delta, (uint32_t)b.ra, (uint32_t)b.rb);
+      // (the minor stride and what only the collision and end steps need share one word: sN | rb<0 | ra | end_delta)
+      sts_u32(at + 512u + 4u * (uint32_t)lane, ((uint32_t)b.sN << 16) | (b.rb < 0 ? 0x1000u : 0u) | ((uint32_t)b.ra << 8) |
+                                                   ((uint32_t)b.end_delta & 0xffu));
       if (lane == 0) sts_v4(at + 1024u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, (org.y & kFrameSorted) ? 1u : 0u);
     };
     if (w < L && w < A.n_frames)
@@ -903,15 +905,16 @@ k_replay_flights(FlightArgs A) {
     __syncthreads();
     for (int f = 0; f < A.n_frames; f++) {
       const uint32_t at = dec_sa + (uint32_t)(f & (R - 1)) * kDecSlotBytes;
-      const uint4 dv = lds_v4(at + 16u * (uint32_t)lane), dw = lds_v4(at + 512u + 16u * (uint32_t)lane);
+      const uint4 dv = lds_v4(at + 16u * (uint32_t)lane);
+      const uint32_t dw = lds_u32(at + 512u + 4u * (uint32_t)lane);
       const uint4 fv = lds_v4(at + 1024u);
       const uint32_t inv = dv.x;
       const int n2 = (int)dv.y, m = (int)dv.z, h2 = m & ~1;
-      const int sM = (int)dv.w, sN = (int)dw.x;
+      const int sM = (int)dv.w, sN = (int)dw >> 16;
       Beam B;
-      B.end_delta = (int)dw.y;
-      B.ra = (int)dw.z;
-      B.rb = (int)dw.w;
+      B.end_delta = (int)(signed char)(dw & 0xffu);
+      B.ra = (int)((dw >> 8) & 0xfu);
+      B.rb = (dw & 0x1000u) ? -1 : 1;
       B.k0 = (int)fv.y;
       const int base = (int)fv.x, mmax = (int)fv.z;
       const bool sorted = fv.w != 0u;
