@@ -67,6 +67,9 @@ def test_fails_loudly_without_a_device(pkg):
     with pytest.raises(pkg.UqsError) as e:
         pkg.replay(p, z, z, z, np.zeros((1, 4, 32), np.float32))
     assert e.value.code == pkg.ERR_NOT_INIT
+    # the profiling exports report "not initialised" too, and the file readers (host-only C) still work
+    assert pkg.lib().uqs_profile_timeline(None, 0) == -1
+    assert pkg.profile_timeline() == []
 
 
 def test_product_never_references_the_oracle():
