@@ -191,6 +191,11 @@ int uqs_pose_integrate_dev(int n_flights, int n_samples,
 int uqs_beam_cells(const uqs_params* p, int n_frames,
                    const float* x, const float* y, const float* yaw_deg, const float* ranges,
                    int32_t* cells_out, int32_t* origin_out);
+/* Parity hook for the collision bound of the resident engine: per frame, K0 (two beams of the frame can share
+ * a cell only at steps k < K0; -1 when the frame's pose is off the grid) and whether the frame's beams were
+ * found in circular angular order.  Host pointers. */
+int uqs_frame_bounds(const uqs_params* p, int n_frames, const float* x, const float* y, const float* yaw_deg,
+                     const float* ranges, int32_t* k0_out, int32_t* sorted_out);
 
 /* Device evaluation of the glibc-2.39 sincosf restatement for n host floats
  * (parity test hook for SURVEY.md Appendix B). */

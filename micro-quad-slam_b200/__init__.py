@@ -82,7 +82,7 @@ _EXPORTS = [
     "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_kernel_launches",
     "uqs_set_profiling", "uqs_profile_collect", "uqs_profile_timeline", "uqs_set_host_chunk",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
-    "uqs_beam_cells", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
+    "uqs_beam_cells", "uqs_frame_bounds", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
     "uqs_beams_from_scans", "uqs_beams_from_scans_dev", "uqs_replay_recentering", "uqs_frontier_scores",
     "uqs_scanlog_read", "uqs_scanlog_count", "uqs_navlog_read", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
     # drop-in symbols
@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
     L.uqs_replay_dev.argtypes = [C.POINTER(Params), ip, ip, vp, vp, vp, vp, vp, ip, ip, ip, C.POINTER(Stats)]
     L.uqs_replay_flow.argtypes = [C.POINTER(Params), ip, ip] + [vp] * 10 + [C.POINTER(Stats)]
     L.uqs_beam_cells.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp]
+    L.uqs_frame_bounds.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp]
     L.uqs_sincosf_batch.argtypes = [C.c_size_t, vp, vp, vp]
     L.uqs_measure_rmw_peak.argtypes = [C.POINTER(C.c_double)]
     L.uqs_beams_from_scans.argtypes = [C.c_longlong, vp, C.c_float, vp, vp]
@@ -300,6 +301,16 @@ def beam_cells(p: Params, x, y, yaw_deg, ranges):
     origin = np.empty((N, 2), np.int32)
     _check(lib().uqs_beam_cells(C.byref(p), N, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(cells), _ptr(origin)))
     return cells, origin
+
+
+def frame_bounds(p: Params, x, y, yaw_deg, ranges):
+    """Collision bound parity hook: (K0 [N], sorted [N]) per frame as the ray set-up writes them (-1 = pose off grid)."""
+    x, y, yaw_deg = _f32(x).ravel(), _f32(y).ravel(), _f32(yaw_deg).ravel()
+    N = x.size
+    ranges = _f32(ranges).reshape(N, BEAMS_PER_FRAME)
+    k0, srt = np.empty(N, np.int32), np.empty(N, np.int32)
+    _check(lib().uqs_frame_bounds(C.byref(p), N, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(k0), _ptr(srt)))
+    return k0, srt
 
 
 def sincosf_batch(ang):

@@ -720,6 +720,46 @@ int uqs_beam_cells(const uqs_params* p, int n_frames, const float* x, const floa
   return UQS_OK;
 }
 
+/* Parity hook for the collision bound: K0 and the angular-order flag of every frame, as k_ray_setup writes
+ * them for the resident engine.  tests/ verify by brute force that no two beams of a frame share a cell at any
+ * step >= K0 and that flagged frames really are in circular angular order. */
+int uqs_frame_bounds(const uqs_params* p, int n_frames, const float* x, const float* y, const float* yaw,
+                     const float* ranges, int32_t* k0_out, int32_t* sorted_out) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_frames <= 0 || !x || !y || !yaw || !ranges || !k0_out || !sorted_out) { set_error("uqs_frame_bounds: bad argument"); return UQS_ERR_BAD_ARG; }
+  if ((rc = ensure_inv_table())) return rc;
+  cudaStream_t st = g_ctx.stream();
+  const size_t n = (size_t)n_frames;
+  const int gpf = (n_frames + 31) / 32;
+  if ((rc = h2d(g_ctx.in_x, x, n * 4, "x H2D")) || (rc = h2d(g_ctx.in_y, y, n * 4, "y H2D")) ||
+      (rc = h2d(g_ctx.in_yaw, yaw, n * 4, "yaw H2D")) || (rc = h2d(g_ctx.in_ranges, ranges, n * 128, "ranges H2D")))
+    return rc;
+  if ((rc = g_ctx.w->rays.ensure(n * 32 * sizeof(uint2))) || (rc = g_ctx.w->frames.ensure(n * sizeof(uint4))) ||
+      (rc = g_ctx.w->groups.ensure((size_t)gpf * sizeof(uint2))) || (rc = g_ctx.w->counters.ensure(64 * 8)))
+    return rc;
+  cudaError_t e = cudaMemsetAsync(g_ctx.w->counters.p, 0, 64, st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset");
+  k_ray_setup<<<(unsigned)gpf, 1024, 0, st>>>(dp, n_frames, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p,
+                                              (float*)g_ctx.in_yaw.p, (float*)g_ctx.in_ranges.p, nullptr, 1,
+                                              (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p,
+                                              (uint2*)g_ctx.w->rays.p, (unsigned long long*)g_ctx.w->counters.p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_ray_setup launch");
+  std::vector<uint4> fr(n);
+  e = cudaMemcpyAsync(fr.data(), g_ctx.w->frames.p, n * sizeof(uint4), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "frame_bounds D2H");
+  for (size_t i = 0; i < n; i++) {
+    k0_out[i] = (fr[i].y & kFrameHasOrigin) ? (int32_t)(fr[i].x >> 16) : -1;       // -1: the frame's pose is off the grid
+    sorted_out[i] = (fr[i].y & kFrameSorted) ? 1 : 0;
+  }
+  g_ctx.launches += 1;
+  return UQS_OK;
+}
+
 int uqs_sincosf_batch(size_t n, const float* ang, float* s, float* c) {
   int rc = check_ready();
   if (rc) return rc;

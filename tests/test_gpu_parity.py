@@ -404,6 +404,78 @@ def test_unaligned_range_log_takes_the_plain_load_path(gpu, oracle, synth):
         gpu.set_stream(None)
 
 
+def _walk_cells(dx, dy):
+    """Cells of the reference's Bresenham walk from (0,0) to (dx,dy) (uav_local_nav.c:246-274), in order."""
+    x = y = 0
+    sx = 1 if dx > 0 else -1
+    sy = 1 if dy > 0 else -1
+    ax, ay = abs(dx), -abs(dy)
+    err = ax + ay
+    out = [(0, 0)]
+    while (x, y) != (dx, dy):
+        e2 = 2 * err
+        if e2 >= ay:
+            err += ay; x += sx
+        if e2 <= ax:
+            err += ax; y += sy
+        out.append((x, y))
+    return out
+
+
+def test_collision_bound_k0_is_safe_by_brute_force(gpu, synth):
+    """The resident engine trusts K0 (k_ray_setup): two beams of a frame may share a cell only at steps k < K0, and
+    frames flagged 'sorted' have their beams in circular angular order.  Both are checked here by brute force on the
+    reference's own walk, for ordinary frames and for hostile ones (very short rays, narrow and wide fans, coarse and
+    fine cells, dropouts), independently of any replay result."""
+    from fractions import Fraction
+    rng = np.random.default_rng(77)
+    checked = shared_below = 0
+    for W, res, fov, rmax in ((400, 0.05, 63.0, 4.0), (200, 0.10, 63.0, 4.0), (800, 0.025, 63.0, 4.0), (400, 0.05, 2.0, 4.0),
+                              (400, 0.05, 170.0, 4.0), (400, 0.05, 89.0, 0.6), (300, 0.07, 120.0, 2.0)):
+        p = gpu.make_params(W, W, res)
+        p.fov_deg = fov
+        p.max_range_m = rmax
+        N = 100
+        x = rng.uniform(-2, 2, N).astype(np.float32)
+        y = rng.uniform(-2, 2, N).astype(np.float32)
+        yaw = rng.uniform(-180, 180, N).astype(np.float32)
+        ranges = rng.uniform(0.06, rmax * 1.1, (N, 32)).astype(np.float32)
+        ranges[rng.random((N, 32)) < 0.1] = np.nan                        # dropouts
+        short = rng.random(N) < 0.3
+        ranges[short] = rng.uniform(0.06, 6 * res, (int(short.sum()), 32)).astype(np.float32)   # rays of a few cells
+        cells, origin = gpu.beam_cells(p, x, y, yaw, ranges)
+        k0, srt = gpu.frame_bounds(p, x, y, yaw, ranges)
+        for f in range(N):
+            if origin[f, 0] < 0:
+                assert k0[f] == -1
+                continue
+            beams = [(b, int(cells[f, b, 0] - origin[f, 0]), int(cells[f, b, 1] - origin[f, 1])) for b in range(32) if cells[f, b, 0] >= 0]
+            walks = {b: _walk_cells(dx, dy) for b, dx, dy in beams}
+            last_shared = -1
+            for i, (bi, _, _) in enumerate(beams):
+                for bj, _, _ in beams[i + 1:]:
+                    wi, wj = walks[bi], walks[bj]
+                    for k in range(min(len(wi), len(wj))):
+                        if wi[k] == wj[k]:
+                            last_shared = max(last_shared, k)
+            assert last_shared < k0[f], (W, fov, f, last_shared, int(k0[f]))
+            checked += 1
+            shared_below += last_shared >= 1
+            if srt[f]:
+                # circular order of the directions: exact position on the unit max-norm ring as a fraction in [0, 8)
+                def sigma(dx, dy):
+                    ax, ay = abs(dx), abs(dy)
+                    if ax >= ay:
+                        t = Fraction(ay, ax)
+                        return (t if dy >= 0 else 8 - t) if dx > 0 else (4 - t if dy >= 0 else 4 + t)
+                    t = Fraction(ax, ay)
+                    return (2 - t if dx >= 0 else 2 + t) if dy > 0 else (6 + t if dx >= 0 else 6 - t)
+                sig = [sigma(dx, dy) % 8 for _, dx, dy in beams if (dx, dy) != (0, 0)]
+                wraps = sum(1 for a, b in zip(sig, sig[1:] + sig[:1]) if b < a)
+                assert wraps <= 1, (W, fov, f, [float(v) for v in sig])
+    assert checked > 500 and shared_below > 250
+
+
 # ----------------------------------------------------------------------------------------------
 # P0
 # ----------------------------------------------------------------------------------------------
