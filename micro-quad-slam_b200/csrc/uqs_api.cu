@@ -281,7 +281,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         *ring = 256;                                        // per-warp collision table (power of two)
         const size_t dec_bytes = (size_t)std::min(w, kDecSlotsMax) * kDecSlotBytes + 16;      // ring of decoded frames (+ alignment)
         while (*ring > 32 && region + (size_t)(*ring + 4) * w + dec_bytes > kFlightSmemMax) *ring >>= 1;
-        *bytes = region + (size_t)(*ring + 4) * w + dec_bytes;         // + one scratch word per warp
+        *bytes = region + (size_t)(*ring + 4) * w + dec_bytes;         // + one spare word per warp
         *ctas = 0;
         return *bytes <= kFlightSmemMax ? flights_prepare(w, *bytes, ctas) : cudaSuccess;
       };

@@ -841,7 +841,7 @@ k_replay_flights(FlightArgs A) {
   const uint32_t const_sa = (uint32_t)__cvta_generic_to_shared(s_const);
   const int lo_free = (int)lds_u32(const_sa), lo_min = (int)lds_u32(const_sa + 4u), lo_max = in_reg(A.lo_max);
   const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
-  // ring of decoded frames (16-byte aligned, after the scratch words)
+  // ring of decoded frames (16-byte aligned, after the collision tables and one spare word per warp)
   const uint32_t dec_sa = (grid_sa + (uint32_t)(P * A.max_rows + NW * A.ring_size + 4 * NW) + 15u) & ~15u;
 
   for (;;) {
@@ -1005,8 +1005,8 @@ k_replay_flights(FlightArgs A) {
         __syncwarp();      // ring[] is rewritten by the next step
       }
 
-      // ---- steps k >= K0: every cell is touched by one beam only; four steps in flight, branch-free
-      // (lanes past their beam's end read-modify-write a scratch byte behind the resident region)
+      // ---- steps k >= K0: every cell is touched by one beam only; UN steps in flight, no branches
+      // (lanes past their beam's end are predicated off)
       int k = B.k0 + ((w - B.k0) & (NW - 1));          // first step >= K0 of this warp's residue class
       const uint32_t gbase = grid_sa + (uint32_t)base;
       const int free_delta = -lo_free;
