@@ -934,6 +934,28 @@ k_replay_flights(FlightArgs A) {
           // consecutive ACTIVE lanes (possibly wrapping from the last to the first), and the -free
           // steps commute, so the head of each run applies the run length at once.
           if (actm0 == 0u) continue;
+          if (actm0 == 0xffffffffu) {
+            // every beam is running (the usual frame): the previous beam is the previous lane, a run ends where
+            // the next head is, and the only run that can wrap is lane 31's into lane 0's
+            const int paddr = __shfl_up_sync(0xffffffffu, addr, 1);
+            const bool head = lane == 0 || paddr != addr;
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            const unsigned above_h = (heads >> 1) >> lane;                            // heads above this lane, shifted down
+            int len = above_h ? __ffs(above_h) : 32 - lane;                           // lanes of my run
+            bool apply = head;
+            const int a_last = __shfl_sync(0xffffffffu, addr, 31);
+            if (heads != 1u && __shfl_sync(0xffffffffu, addr, 0) == a_last) {         // lane 0's run continues lane 31's
+              const int len0 = __shfl_sync(0xffffffffu, len, 0);
+              if (lane == 31 - __clz(heads)) len += len0;
+              if (lane == 0) apply = false;
+            }
+            if (apply) {
+              const uint32_t cell = grid_sa + (uint32_t)addr;
+              sts_u8(cell, max(lds_s8(cell) - len * lo_free, lo_min));
+            }
+            __syncwarp();
+            continue;
+          }
           const unsigned lower = actm0 & ((1u << lane) - 1u);
           const int prev = lower ? (31 - __clz(lower)) : lane;
           const int paddr = __shfl_sync(0xffffffffu, addr, prev);
