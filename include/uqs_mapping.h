@@ -65,9 +65,12 @@ enum {
   UQS_ERR_CUDA = 2,          /* a CUDA call or kernel failed; see uqs_last_error() */
   UQS_ERR_BAD_ARG = 3,       /* NULL pointer, non-positive size, bad params        */
   UQS_ERR_NOT_INIT = 4,      /* uqs_init() has not succeeded                       */
-  UQS_ERR_DOMAIN = 5,        /* an input left the domain the exact arithmetic covers
-                                (|angle| >= 120 rad or ray longer than 1024 cells) */
-  UQS_ERR_NOMEM = 6
+  UQS_ERR_DOMAIN = 5,        /* internal consistency failure: a ray reached an engine that cannot represent
+                                it.  No input raises it since every float angle (glibc's reduce_large branch
+                                included) and every ray length is covered -- see uqs_set_engine() */
+  UQS_ERR_NOMEM = 6,
+  UQS_ERR_NO_NCCL = 7,       /* libnccl.so.2 could not be loaded (multi-GPU entry points only) */
+  UQS_ERR_NCCL = 8           /* an NCCL call failed; see uqs_last_error()                       */
 };
 
 /* Counters returned by the replay calls.  All exact integers. */
@@ -120,9 +123,15 @@ int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
 /* Replay engine: 0 = automatic (each flight's touched bounding box resident in one CTA's
  * shared memory when several such CTAs fit an SM and there is at least one flight per
  * SM; warp-owned sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
- * (error if the flights' touched bounding box does not fit).  flight_warps = warps
- * per CTA of the resident engine (0 = automatic, 4, 8, 16 or 32).  Both engines
- * produce identical bytes. */
+ * (error if the flights' touched bounding box does not fit), 3 = always the unrestricted
+ * kernel.  flight_warps = warps per CTA of the resident engine (0 = automatic, 4, 8, 16
+ * or 32).  All engines produce identical bytes.
+ * The unrestricted kernel (one warp per flight on the grid in global memory, the
+ * reference's loop statement for statement) is what engines 0-2 route to by themselves
+ * for the inputs their fast paths do not cover: rays that can exceed 1024 cells
+ * (max_range_m / res_m > 1021 on a grid wider than 1025 cells, or raycast_update() on
+ * such a grid), a clamp range that excludes 0, and accumulate != 0 onto a grid holding
+ * values outside [lo_min, lo_max].  Nothing is refused or approximated. */
 int  uqs_set_engine(int engine, int flight_warps);
 
 /*
@@ -238,6 +247,55 @@ long uqs_scanlog_count(const char* path, int keep_nan_pose);
 long uqs_navlog_read(const char* path, long max_rows, uint32_t* t_ms, float* yaw_deg, float* alt_m, float* x_m,
                      float* y_m, float* vx_mps, float* vy_mps, float* rf_m, uint8_t* of_q, float* of_rate_x,
                      float* of_rate_y, float* tof4);
+
+/* ------------------------------------------------------------------------ */
+/* Multi-GPU                                        */
+/* ------------------------------------------------------------------------ */
+/* Partitions -- host arithmetic only, usable without a device.
+ *   uqs_flight_shard: contiguous block [first, first+count) of n_flights independent flights for `rank`
+ *                     (configs 3 and 5: every GPU replays its own flights into its own grids; no collective).
+ *   uqs_row_band:     rows [row0, row0+rows) of an H-row grid OWNED by `rank`, edges multiples of `align`
+ *                     (config 4: occ_grid, uav_local_nav.c:188, split across GPUs.  The reference clamps after
+ *                     every update, :259-260, so partial grids cannot be summed; owned bands are exact). */
+void uqs_flight_shard(int n_flights, int rank, int world, int* first, int* count);
+void uqs_row_band(int H, int rank, int world, int align, int* row0, int* rows);
+
+/* (i) One process per GPU.  Rank 0 calls uqs_comm_unique_id(), the launcher broadcasts the 128 bytes by its own
+ * means, every rank calls uqs_comm_init_rank() after uqs_init(local device) (ncclCommInitRank underneath;
+ * NCCL is loaded at run time with dlopen, UQS_ERR_NO_NCCL if absent). */
+#define UQS_COMM_ID_BYTES 128
+int uqs_comm_unique_id(void* id128);
+int uqs_comm_init_rank(const void* id128, int nranks, int rank);
+int uqs_comm_destroy(void);
+int uqs_comm_nranks(void);
+int uqs_comm_rank(void);
+int uqs_nccl_version(void);            /* e.g. 22809; 0 if NCCL cannot be loaded */
+/* Config 4 on this rank: replay this rank's owned row band of ONE W x H grid from a log that every rank holds
+ * on its device, then (gather != 0) the path's single exchange: the disjoint bands are all-gathered over NCCL so
+ * that every rank holds the whole grid.  grid_dev addresses the full W*H grid.  Asynchronous on the current
+ * stream unless stats is given.  Without a communicator this is a whole-grid replay (1 rank). */
+int uqs_replay_banded_dev(const uqs_params* p, int n_frames, const float* x_dev, const float* y_dev,
+                          const float* yaw_dev, const float* ranges_dev, int8_t* grid_dev, int gather,
+                          uqs_stats* stats);
+/* Host-buffer form: every rank passes the same log; rank r uploads only slice r over PCIe, the slices are
+ * all-gathered over NVLink, then as above with the gather; grid_out (NULL on ranks that do not want it)
+ * receives the whole grid.  Synchronous. */
+int uqs_replay_banded(const uqs_params* p, int n_frames, const float* x, const float* y, const float* yaw_deg,
+                      const float* ranges, int8_t* grid_out, uqs_stats* stats);
+
+/* (ii) One host thread driving N devices (what a plain C harness does; ncclCommInitAll underneath).
+ * uqs_multi_init() creates one device context per GPU (devices == NULL: 0..n-1); uqs_multi_select(i) makes
+ * context i current, after which EVERY single-device call of this header addresses device i (flight shards:
+ * select, enqueue uqs_replay_dev on the shard, next device; then uqs_sync each).  uqs_multi_replay_banded() is
+ * config 4 end to end from host buffers: slices up on N PCIe links, log all-gather, owned bands, band
+ * all-gather, bands down on N links, nothing blocking between devices. */
+int  uqs_multi_init(int n_devices, const int* devices);
+int  uqs_multi_count(void);
+int  uqs_multi_select(int i);
+void uqs_multi_shutdown(void);
+int  uqs_multi_replay_banded(const uqs_params* p, int n_frames, const float* x, const float* y,
+                             const float* yaw_deg, const float* ranges, int8_t* grid_out, uqs_stats* stats);
+const int8_t* uqs_multi_grid_dev(int i);   /* device i's copy of the whole grid after the call above */
 
 /* Measured on-chip read-modify-write ceiling: every warp of a full grid does
  * conflict-free byte RMWs on its shared-memory sub-tile.  Returns updates/s. */

@@ -24,7 +24,8 @@ SYNTH_LIB_PATH = os.path.join(_HERE, "libuqs_synth.so")
 
 BEAMS_PER_FRAME = 32
 
-OK, ERR_NO_DEVICE, ERR_CUDA, ERR_BAD_ARG, ERR_NOT_INIT, ERR_DOMAIN, ERR_NOMEM = range(7)
+OK, ERR_NO_DEVICE, ERR_CUDA, ERR_BAD_ARG, ERR_NOT_INIT, ERR_DOMAIN, ERR_NOMEM, ERR_NO_NCCL, ERR_NCCL = range(9)
+COMM_ID_BYTES = 128
 
 
 class UqsError(RuntimeError):
@@ -85,6 +86,10 @@ _EXPORTS = [
     "uqs_beam_cells", "uqs_frame_bounds", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
     "uqs_beams_from_scans", "uqs_beams_from_scans_dev", "uqs_replay_recentering", "uqs_frontier_scores",
     "uqs_scanlog_read", "uqs_scanlog_count", "uqs_navlog_read", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
+    # multi-GPU
+    "uqs_flight_shard", "uqs_row_band", "uqs_comm_unique_id", "uqs_comm_init_rank", "uqs_comm_destroy", "uqs_comm_nranks",
+    "uqs_comm_rank", "uqs_nccl_version", "uqs_replay_banded_dev", "uqs_replay_banded", "uqs_multi_init", "uqs_multi_count",
+    "uqs_multi_select", "uqs_multi_shutdown", "uqs_multi_replay_banded", "uqs_multi_grid_dev",
     # drop-in symbols
     "uqs_dropin_configure", "uqs_dropin_flush", "uqs_dropin_upload", "map_reset",
     "occ_grid", "map_inited", "map_origin_x", "map_origin_y", "tof_beams_m", "pending_kf_flags",
@@ -133,6 +138,20 @@ def lib() -> C.CDLL:
     L.uqs_scanlog_count.argtypes = [C.c_char_p, ip]
     L.uqs_navlog_read.restype = C.c_long
     L.uqs_navlog_read.argtypes = [C.c_char_p, C.c_long] + [vp] * 12
+    L.uqs_flight_shard.argtypes = [ip, ip, ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.uqs_flight_shard.restype = None
+    L.uqs_row_band.argtypes = [ip, ip, ip, ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.uqs_row_band.restype = None
+    L.uqs_comm_unique_id.argtypes = [vp]
+    L.uqs_comm_init_rank.argtypes = [vp, ip, ip]
+    L.uqs_replay_banded_dev.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, ip, C.POINTER(Stats)]
+    L.uqs_replay_banded.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.uqs_multi_init.argtypes = [ip, C.POINTER(C.c_int)]
+    L.uqs_multi_select.argtypes = [ip]
+    L.uqs_multi_shutdown.restype = None
+    L.uqs_multi_replay_banded.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.uqs_multi_grid_dev.argtypes = [ip]
+    L.uqs_multi_grid_dev.restype = C.c_void_p
     L.map_recenter_shift.argtypes = [ip, ip]
     L.map_recenter_shift.restype = None
     L.map_recentre_if_needed.argtypes = [C.c_float, C.c_float]
@@ -384,6 +403,95 @@ def scanlog_read(path: str, keep_nan_pose: bool = False) -> dict:
     if got != n:
         raise UqsError(ERR_BAD_ARG, f"scan log changed while reading ({got} != {n})")
     return d
+
+
+# ---- multi-GPU (include/uqs_mapping.h, "Multi-GPU") ------------------------------------------------------------
+def flight_shard(n_flights: int, rank: int, world: int):
+    """``uqs_flight_shard``: [first, count) of the flights ``rank`` replays (host arithmetic, no device needed)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    a, b = C.c_int(0), C.c_int(0)
+    lib().uqs_flight_shard(int(n_flights), int(rank), int(world), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def row_band(H: int, rank: int, world: int, align: int = 4):
+    """``uqs_row_band``: [row0, rows) of the grid rows ``rank`` owns (host arithmetic, no device needed)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    a, b = C.c_int(0), C.c_int(0)
+    lib().uqs_row_band(int(H), int(rank), int(world), int(align), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().uqs_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init_rank(uid: bytes, nranks: int, rank: int):
+    if len(uid) != COMM_ID_BYTES:
+        raise ValueError("the communicator id is 128 bytes")
+    _check(lib().uqs_comm_init_rank(C.create_string_buffer(uid, COMM_ID_BYTES), int(nranks), int(rank)))
+
+
+def comm_destroy():
+    _check(lib().uqs_comm_destroy())
+
+
+def comm_nranks() -> int:
+    return int(lib().uqs_comm_nranks())
+
+
+def nccl_version() -> int:
+    return int(lib().uqs_nccl_version())
+
+
+def replay_banded_dev(p: Params, n_frames: int, x_ptr: int, y_ptr: int, yaw_ptr: int, ranges_ptr: int, grid_ptr: int,
+                      gather: bool = True, want_stats: bool = False):
+    """``uqs_replay_banded_dev``: this rank's owned row band of one grid, then the all-gather of the bands."""
+    st = Stats()
+    _check(lib().uqs_replay_banded_dev(C.byref(p), int(n_frames), C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.c_void_p(yaw_ptr),
+                                       C.c_void_p(ranges_ptr), C.c_void_p(grid_ptr), 1 if gather else 0,
+                                       C.byref(st) if want_stats else None))
+    return st.as_dict() if want_stats else None
+
+
+def replay_banded(p: Params, x, y, yaw_deg, ranges, out: Optional[np.ndarray] = None, want_grid: bool = True):
+    """``uqs_replay_banded`` (host buffers, one process per GPU): returns (grid or None, stats)."""
+    x, y, yaw_deg = _f32(x).ravel(), _f32(y).ravel(), _f32(yaw_deg).ravel()
+    n = x.size
+    ranges = _f32(ranges).reshape(n, BEAMS_PER_FRAME)
+    grid = (out if out is not None else np.empty((p.H, p.W), np.int8)) if want_grid else None
+    st = Stats()
+    _check(lib().uqs_replay_banded(C.byref(p), n, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges),
+                                   _ptr(grid) if grid is not None else None, C.byref(st)))
+    return grid, st.as_dict()
+
+
+def multi_init(n_devices: int, devices=None):
+    arr = (C.c_int * n_devices)(*devices) if devices is not None else None
+    _check(lib().uqs_multi_init(int(n_devices), arr))
+
+
+def multi_select(i: int):
+    _check(lib().uqs_multi_select(int(i)))
+
+
+def multi_shutdown():
+    lib().uqs_multi_shutdown()
+
+
+def multi_replay_banded(p: Params, x, y, yaw_deg, ranges, out: Optional[np.ndarray] = None):
+    """``uqs_multi_replay_banded``: config 4 on every device of ``multi_init`` from one host thread."""
+    x, y, yaw_deg = _f32(x).ravel(), _f32(y).ravel(), _f32(yaw_deg).ravel()
+    n = x.size
+    ranges = _f32(ranges).reshape(n, BEAMS_PER_FRAME)
+    grid = out if out is not None else np.empty((p.H, p.W), np.int8)
+    st = Stats()
+    _check(lib().uqs_multi_replay_banded(C.byref(p), n, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(grid), C.byref(st)))
+    return grid, st.as_dict()
 
 
 def measure_rmw_peak() -> float:

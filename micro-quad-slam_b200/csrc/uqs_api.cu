@@ -16,7 +16,8 @@
 
 namespace uqs {
 
-Context g_ctx;
+static Context g_single;            // the context of uqs_init(); uqs_multi.cu owns the others
+Context* g_cur = &g_single;
 
 static char g_err[512] = "";
 
@@ -113,7 +114,11 @@ int ensure_inv_table() {
   for (uint32_t m = 1; m <= (uint32_t)kMaxRayCells; m++) t[m] = (uint32_t)(((1ull << 31) + m - 1) / m);
   int rc = g_ctx.inv_table.ensure(t.size() * sizeof(uint32_t));
   if (rc) return rc;
-  cudaError_t e = cudaMemcpy(g_ctx.inv_table.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  // on the stream the kernels run on (non-blocking streams are not ordered against the legacy stream), and
+  // complete before the pageable source goes out of scope
+  cudaError_t e = cudaMemcpyAsync(g_ctx.inv_table.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g_ctx.stream());
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream());
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();     // visible to every stream of the library (pipeline, caller's)
   if (e != cudaSuccess) { g_ctx.inv_table.release(); return cuda_fail(e, "inv table upload"); }
   return UQS_OK;
 }
@@ -151,6 +156,37 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   {
     const int rc0 = ensure_inv_table();
     if (rc0) return rc0;
+  }
+  // Inputs outside what the fast engines assume go to the unrestricted kernel (uqs_generic.cu): rays that can be
+  // longer than kMaxRayCells cells, a clamp range that excludes 0, or -- when accumulating -- a start grid with
+  // values outside [lo_min, lo_max] (checked on the device; the reference clamps such a cell on its next update).
+  {
+    const int side = std::max(dp.W, dp.H);
+    const bool long_rays = side > kMaxRayCells + 1 && (kind != nullptr || !(dp.max_range / dp.res + 3.0f <= (float)kMaxRayCells));
+    bool generic = g_ctx.engine == 3 || long_rays || dp.lo_min > 0 || dp.lo_max < 0;
+    int rcg;
+    if ((rcg = g_ctx.w->counters.ensure(64 * sizeof(unsigned long long)))) return rcg;
+    unsigned long long* cnt = (unsigned long long*)g_ctx.w->counters.p;
+    cudaError_t eg = cudaSuccess;
+    if (!generic && accumulate) {
+      unsigned long long bad = 0;
+      eg = zero_counted(cnt + 40, sizeof(unsigned long long), st);
+      if (eg == cudaSuccess) eg = range_check_launch(grids, n_flights, dp.W, dp.H, row0, rows, dp.lo_min, dp.lo_max, cnt + 40, st);
+      if (eg == cudaSuccess) eg = cudaMemcpyAsync(&bad, cnt + 40, sizeof(bad), cudaMemcpyDeviceToHost, st);
+      if (eg == cudaSuccess) eg = cudaStreamSynchronize(st);
+      if (eg != cudaSuccess) return cuda_fail(eg, "start-grid range check");
+      g_ctx.launches += 1;
+      generic = bad != 0;
+    }
+    if (generic) {
+      if (reset_stats) eg = zero_counted(cnt, 8 * sizeof(unsigned long long), st);
+      KernelTimer t_rep(2);
+      if (eg == cudaSuccess) eg = generic_launch(dp, n_flights, n_frames, x, y, yaw, ranges, kind, grids, accumulate, row0, rows, cnt, st);
+      t_rep.stop();
+      if (eg != cudaSuccess) return cuda_fail(eg, "k_replay_generic launch");
+      g_ctx.launches += accumulate ? 1 : 2;
+      return UQS_OK;
+    }
   }
   // Sub-tile engine geometry.  With plenty of (flight, tile) jobs, ~80-cell tiles and no time slicing.
   // With few (one long log, one small flight) the chip would idle: cut the log into S time slices,
@@ -205,7 +241,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
   // bookkeeping is paid per warp -- more warps per CTA when flights are scarce
   // (chunks of the host-buffer pipeline overlap on two streams and fill the chip together: 4 as well)
   const int nw = g_ctx.flight_warps ? g_ctx.flight_warps
-                 : ((n_flights >= 4 * g_ctx.sm_count || g_ctx.w != &g_ctx.works[0]) ? 4 : (n_flights >= 2 * g_ctx.sm_count ? 8 : 16));
+                 : ((n_flights >= 4 * g_ctx.sm_count || g_ctx.chip_shared) ? 4 : (n_flights >= 2 * g_ctx.sm_count ? 8 : 16));
   const bool may_reside = g_ctx.engine != 1 && row0 == 0 && rows == dp.H;
   if (g_ctx.engine == 2 && !may_reside) {
     set_error("engine 2 (resident) cannot replay a row band");
@@ -308,7 +344,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       // 16 warps per SM it still beats the sub-tile engine by 1.6x on the 668^2 and 800^2 grids of config 5);
       // otherwise the sub-tile engine (time-sliced when flights are few)
       // (a chunk of the host-buffer pipeline shares the chip with its neighbours: no flight-count condition there)
-      const bool pipelined = g_ctx.w != &g_ctx.works[0];
+      const bool pipelined = g_ctx.chip_shared;               // other chunks of a host-buffer call share the chip
       const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || nf >= g_ctx.sm_count || pipelined);
       if (resident) {
         FlightArgs FA;
@@ -417,7 +453,7 @@ int fetch_stats_mask(uqs_stats* stats, uint64_t frames, unsigned mask) {
   stats->domain_errors = tot[3];
   stats->frames = frames;
   if (tot[3]) {
-    set_error("%llu rays left the exact-arithmetic domain (|angle| >= 120 rad or > %d cells)", tot[3], kMaxRayCells);
+    set_error("%llu rays longer than %d cells reached a fast engine (internal routing error)", tot[3], kMaxRayCells);
     return UQS_ERR_DOMAIN;
   }
   return UQS_OK;
@@ -466,6 +502,54 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
   return UQS_OK;
 }
 
+void context_select_single() {
+  g_cur = &g_single;
+  if (g_single.ready) cudaSetDevice(g_single.device);
+}
+
+int context_init(Context& c, int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    c.ready = false;
+    return UQS_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return UQS_ERR_BAD_ARG; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return UQS_ERR_NO_DEVICE;
+  }
+  if ((e = cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return cuda_fail(e, "cudaStreamCreate");
+  c.device = device;
+  c.sm_count = prop.multiProcessorCount;
+  c.ext_stream = nullptr;
+  c.use_ext = false;
+  c.ready = true;
+  g_err[0] = 0;
+  return UQS_OK;
+}
+
+// the caller makes `c` current first (the release helpers act on the current context)
+void context_shutdown(Context& c) {
+  if (!c.ready) return;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  comm_release();
+  dropin_release();
+  pipeline_release();
+  c.release_all();
+  if (c.own_stream) cudaStreamDestroy(c.own_stream);
+  c.own_stream = nullptr;
+  c.ready = false;
+}
+
 }  // namespace uqs
 
 using namespace uqs;
@@ -484,46 +568,20 @@ void uqs_params_default(uqs_params* p) {
 const char* uqs_last_error(void) { return g_err; }
 
 int uqs_init(int device) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0) {
-    cudaGetLastError();
-    set_error("no CUDA device available (%s); this library has no CPU fallback",
-              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    g_ctx.ready = false;
-    return UQS_ERR_NO_DEVICE;
+  g_cur = &g_single;
+  if (g_single.ready && g_single.device == device) {
+    cudaSetDevice(device);
+    return UQS_OK;
   }
-  if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return UQS_ERR_BAD_ARG; }
-  if (g_ctx.ready && g_ctx.device == device) return UQS_OK;
-  if (g_ctx.ready) uqs_shutdown();
-  if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  cudaDeviceProp prop;
-  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
-  if (prop.major < 10) {
-    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    return UQS_ERR_NO_DEVICE;
-  }
-  if ((e = cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking)) != cudaSuccess)
-    return cuda_fail(e, "cudaStreamCreate");
-  g_ctx.device = device;
-  g_ctx.sm_count = prop.multiProcessorCount;
-  g_ctx.ext_stream = nullptr;
-  g_ctx.use_ext = false;
-  g_ctx.ready = true;
-  g_err[0] = 0;
-  return UQS_OK;
+  if (g_single.ready) uqs_shutdown();
+  return context_init(g_single, device);
 }
 
 void uqs_shutdown(void) {
-  if (!g_ctx.ready) return;
-  cudaSetDevice(g_ctx.device);
-  cudaDeviceSynchronize();
-  dropin_release();
-  pipeline_release();
-  g_ctx.release_all();
-  if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
-  g_ctx.own_stream = nullptr;
-  g_ctx.ready = false;
+  Context* saved = g_cur;
+  g_cur = &g_single;
+  context_shutdown(g_single);
+  g_cur = (saved == &g_single) ? &g_single : saved;
 }
 
 int uqs_device_sm_count(void) { return g_ctx.ready ? g_ctx.sm_count : 0; }
@@ -560,8 +618,8 @@ int uqs_set_tuning(int sw, int sh, int time_slices) {
 }
 
 int uqs_set_engine(int engine, int flight_warps) {
-  if (engine < 0 || engine > 2 || (flight_warps != 0 && flight_warps != 4 && flight_warps != 8 && flight_warps != 16 && flight_warps != 32)) {
-    set_error("engine must be 0 (auto), 1 (sub-tiles) or 2 (grid resident); warps 0, 4, 8, 16 or 32");
+  if (engine < 0 || engine > 3 || (flight_warps != 0 && flight_warps != 4 && flight_warps != 8 && flight_warps != 16 && flight_warps != 32)) {
+    set_error("engine must be 0 (auto), 1 (sub-tiles), 2 (grid resident) or 3 (unrestricted); warps 0, 4, 8, 16 or 32");
     return UQS_ERR_BAD_ARG;
   }
   g_ctx.engine = engine;

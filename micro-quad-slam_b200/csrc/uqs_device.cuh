@@ -36,15 +36,67 @@ constexpr uint32_t kFrameSorted    = 1u << 17;   // the frame's beams are in cir
 constexpr uint32_t kEmptyBoxLoHi  = 0x00007fffu;  // min = 0x7fff, max = 0  -> never overlaps
 
 // ---------------------------------------------------------------------------
-// glibc 2.39 sincosf, FMA build, restated.  Returns false
-// when |y| >= 120 or y is not finite: that branch (reduce_large) is not restated,
-// the caller must drop the ray and raise UQS_ERR_DOMAIN.
+// glibc 2.39 sincosf, FMA build, restated: all three branches, so every
+// float input gives libm's bits.  |y| < 120 is the straight-line path below; |y| >= 120 is glibc's
+// reduce_large (24-bit mantissa x 96 bits of 2/pi in integer arithmetic) -- the CPU restatement of the same
+// code equals libm on every float (tests/test_arith_kats.py); Inf/NaN give y - y
+// with x86's NaN bits (they only matter to the parity hook: lrintf of any NaN is the same cell).
+// Always returns true (kept for callers that still test it).
 // ---------------------------------------------------------------------------
+static __constant__ uint32_t kInvPio4[24] = {
+  0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27,
+  0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62, 0xc0db6295,
+  0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041 };
+
+// the polynomial tail shared by both reductions: x reduced, xs = x with the quadrant's sign, swap = n & 1,
+// neg_cos = the second coefficient table (cosine coefficients negated)
+__device__ __forceinline__ void sincosf_poly(double x, double xs, bool swap, bool neg_cos, float& sn, float& cs) {
+  const double x2 = __dmul_rn(x, x);
+  const double x3 = __dmul_rn(x2, xs);
+  const double x4 = __dmul_rn(x2, x2);
+  const double s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+  const double c2 = __fma_rn(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
+  const double c1 = __fma_rn(x2, -0x1.ffffffd0c621cp-2, 1.0);
+  const double x5 = __dmul_rn(x2, x3);
+  const double x6 = __dmul_rn(x2, x4);
+  double S = __fma_rn(x3, -0x1.555545995a603p-3, xs);
+  double C = __fma_rn(x4, 0x1.55553e1068f19p-5, c1);
+  S = __fma_rn(x5, s1, S);
+  C = __fma_rn(x6, c2, C);
+  if (neg_cos) C = -C;
+  const float fs = __double2float_rn(S), fc = __double2float_rn(C);
+  if (swap) { cs = fs; sn = fc; } else { sn = fs; cs = fc; }
+}
+
+static __device__ __noinline__ void sincosf_large(float y, float& sn, float& cs) {
+  uint32_t xi = __float_as_uint(y);
+  if (((xi >> 20) & 0x7ffu) >= 0x7f8u) {       // Inf, NaN: y - y as x86 computes it
+    const uint32_t nan = ((xi & 0x7fffffffu) == 0x7f800000u) ? 0xffc00000u : (xi | 0x00400000u);
+    sn = cs = __uint_as_float(nan);
+    return;
+  }
+  const int sign = (int)(xi >> 31);
+  const uint32_t* arr = &kInvPio4[(xi >> 26) & 15u];
+  const int shift = (int)((xi >> 23) & 7u);
+  xi = ((xi & 0xffffffu) | 0x800000u) << shift;
+  unsigned long long res0 = (unsigned long long)(uint32_t)(xi * arr[0]);
+  const unsigned long long res1 = (unsigned long long)xi * arr[4];
+  const unsigned long long res2 = (unsigned long long)xi * arr[8];
+  res0 = (res2 >> 32) | (res0 << 32);
+  res0 += res1;
+  const unsigned long long nn = (res0 + (1ull << 61)) >> 62;
+  res0 -= nn << 62;
+  const double x = __dmul_rn(__ll2double_rn((long long)res0), 0x1.921FB54442D18p-62);
+  const int n = (int)nn;
+  const double xs = (((n + sign) + 1) & 2) ? -x : x;          // sign table {+,-,-,+}[(n + sign) & 3]
+  sincosf_poly(x, xs, (n & 1) != 0, ((n + sign) & 2) != 0, sn, cs);
+}
+
 __device__ __forceinline__ bool sincosf_glibc(float y, float& sn, float& cs) {
   const uint32_t top12 = (__float_as_uint(y) >> 20) & 0x7ffu;
-  if (top12 >= 0x42fu) {                      // |y| >= 120, Inf, NaN
-    sn = cs = __int_as_float(0x7fc00000);
-    return false;
+  if (top12 >= 0x42fu) {                      // |y| >= 120, Inf, NaN: the rare branch, out of line
+    sincosf_large(y, sn, cs);
+    return true;
   }
   // glibc skips the reduction when |y| < 0.75 (top12 < 0x3f4); running it there gives n = 0 and leaves x
   // unchanged bit for bit (|y * 2/pi| < 0.48 rounds to 0, fma(-0.0, pi/2, x) == x), so one straight-line

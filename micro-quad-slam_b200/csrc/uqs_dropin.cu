@@ -40,6 +40,7 @@ struct DropIn {
   int count = 0;
   float snap_ox = 0.f, snap_oy = 0.f;   // origin the queued entries were issued under
   bool mirror_stale = false;
+  Context* owner = nullptr;      // the device context the drop-in map lives on (the one current at configure time)
 } D;
 
 [[noreturn]] void die(const char* what) {
@@ -70,8 +71,8 @@ int flush_queue() {
   rc = replay_device(dp, 1, D.count, (float*)g_ctx.in_x.p, (float*)g_ctx.in_y.p, (float*)g_ctx.in_yaw.p,
                      (float*)g_ctx.in_ranges.p, (uint8_t*)g_ctx.in_kind.p, D.d_grid, 1, 0, p.H, true);
   if (rc) return rc;
-  e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return cuda_fail(e, "drop-in replay");
+  uqs_stats qs;
+  if ((rc = fetch_stats(&qs, n))) return rc;             // synchronises; a dropped ray is an error, never silent
   D.count = 0;
   D.mirror_stale = true;
   return UQS_OK;
@@ -91,6 +92,7 @@ void enqueue(uint8_t kind, float a, float b, float c, const float* r32) {
 }  // namespace
 
 void dropin_release() {
+  if (D.owner && D.owner != g_cur) return;      // another device's context is shutting down
   if (D.d_grid) cudaFree(D.d_grid);
   if (occ_grid) cudaFreeHost(occ_grid);
   if (D.qx) cudaFreeHost(D.qx);
@@ -115,6 +117,7 @@ int uqs_dropin_configure(const uqs_params* p) {
   if (rc == UQS_ERR_NOT_INIT && (rc = uqs_init(0))) return rc;
   DevParams dp;
   if ((rc = make_dev_params(p, &dp))) return rc;
+  D.owner = nullptr;               // reconfiguring: whatever device held the old map, free it
   dropin_release();
   const size_t cells = (size_t)p->W * p->H;
   cudaError_t e = cudaMalloc(&D.d_grid, cells);
@@ -133,6 +136,7 @@ int uqs_dropin_configure(const uqs_params* p) {
   }
   memset(occ_grid, 0, cells);
   D.cfg = *p;
+  D.owner = g_cur;
   D.configured = true;
   map_origin_x = p->origin_x;
   map_origin_y = p->origin_y;

@@ -45,6 +45,7 @@ struct Context {
   int engine = 0;                               // 0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA
   int flight_warps = 0;                         // warps per CTA of the resident engine (0 = 16)
   int host_chunk = 0;                           // flights per chunk of the host-buffer pipeline (0 = auto)
+  bool chip_shared = false;                     // a multi-chunk host-buffer call is in flight: chunks share the chip
   size_t scratch_budget = (size_t)12 << 30;     // ray/frame records held at once
   unsigned long long launches = 0;              // kernels launched by this library
   DevBuf inv_table;                             // ceil(2^31 / m) for m = 0..kMaxRayCells (0 at m = 0)
@@ -53,6 +54,9 @@ struct Context {
   Work* w = &works[0];
   // staging for the host-buffer entry points
   DevBuf in_t, in_rx, in_ry, in_h, in_yaw, in_q, in_x, in_y, in_ranges, in_kind, out_grids;
+  void* pipeline = nullptr;                     // streams and staging of the host-buffer pipeline (uqs_pipeline.cu)
+  void* comm = nullptr;                         // ncclComm_t of this device (uqs_multi.cu), nullptr = none
+  int comm_rank = 0, comm_nranks = 1;
 
   // optional per-kernel timing (uqs_set_profiling): event pairs on the launching stream
   bool profiling = false;
@@ -71,7 +75,14 @@ struct Context {
 
 constexpr size_t kFlightSmemMax = 227u * 1024u - 64u;   // dynamic + the kernel's few static bytes
 
-extern Context g_ctx;
+// One Context per device.  A process that drives one GPU (the usual case: one process per GPU) only ever has the
+// first; uqs_multi_init() creates one per device and uqs_multi_select() switches the current one, so every entry
+// point below works unchanged on whichever device is current.
+extern Context* g_cur;
+#define g_ctx (*::uqs::g_cur)
+int context_init(Context& c, int device);     // stream + properties on `device` (leaves it current)
+void context_shutdown(Context& c);
+void context_select_single();                 // back to the context of uqs_init()
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
@@ -82,9 +93,16 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
                   int accumulate, int row0, int rows, bool reset_stats);
 int fetch_stats(uqs_stats* stats, uint64_t frames);
 int ensure_inv_table();
+// uqs_generic.cu: the unrestricted replay and the start-grid range check
+cudaError_t generic_launch(const DevParams& dp, int n_flights, int n_frames, const float* x, const float* y, const float* yaw,
+                           const float* ranges, const uint8_t* kind, int8_t* grids, int accumulate, int row0, int rows,
+                           unsigned long long* stats, cudaStream_t st);
+cudaError_t range_check_launch(const int8_t* grids, int n_flights, int W, int H, int row0, int rows, int lo_min, int lo_max,
+                               unsigned long long* bad, cudaStream_t st);
 int fetch_stats_mask(uqs_stats* stats, uint64_t frames, unsigned mask);
 void dropin_release();
 void pipeline_release();
+void comm_release();                          // uqs_multi.cu: destroys the current context's communicator
 int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float* rx, const float* ry,
                 const float* h, const float* yaw, const uint8_t* q, float* xo, float* yo, int mode);
 

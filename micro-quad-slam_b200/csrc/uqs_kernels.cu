@@ -31,7 +31,7 @@ __global__ void k_pose_increments(long long total, int n_samples, const uint32_t
                                   const float* __restrict__ h_m, const float* __restrict__ yaw_deg,
                                   const uint8_t* __restrict__ q, float deg2rad,
                                   float* __restrict__ inc_n, float* __restrict__ inc_e,
-                                  unsigned long long* __restrict__ domain_errors) {
+                                  unsigned long long* __restrict__ /*unused*/) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int s = (int)(i % n_samples);
@@ -44,14 +44,11 @@ __global__ void k_pose_increments(long long total, int n_samples, const uint32_t
       const float vby = __fmul_rn(ry, h);
       const float a = __fmul_rn(yw, deg2rad);
       float sn, cs;
-      if (sincosf_glibc(a, sn, cs)) {
-        const float vn = __fsub_rn(__fmul_rn(vbx, cs), __fmul_rn(vby, sn));
-        const float ve = __fadd_rn(__fmul_rn(vbx, sn), __fmul_rn(vby, cs));
-        dn = __fmul_rn(vn, dt);
-        de = __fmul_rn(ve, dt);
-      } else {
-        atomicAdd(domain_errors, 1ull);
-      }
+      sincosf_glibc(a, sn, cs);                                  // every float: Inf yaw gives NaN poses, like libm
+      const float vn = __fsub_rn(__fmul_rn(vbx, cs), __fmul_rn(vby, sn));
+      const float ve = __fadd_rn(__fmul_rn(vbx, sn), __fmul_rn(vby, cs));
+      dn = __fmul_rn(vn, dt);
+      de = __fmul_rn(ve, dt);
     }
   }
   inc_n[i] = dn;

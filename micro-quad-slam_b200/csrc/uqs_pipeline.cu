@@ -27,7 +27,14 @@ struct Pipeline {
   bool made = false;
   cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = { nullptr, nullptr };
   Stage st[kStages];
-} P;
+};
+
+// one pipeline per device context, created on first use
+Pipeline& pipe() {
+  if (!g_ctx.pipeline) g_ctx.pipeline = new Pipeline();
+  return *static_cast<Pipeline*>(g_ctx.pipeline);
+}
+#define P pipe()
 
 int pipeline_init() {
   if (P.made) return UQS_OK;
@@ -48,6 +55,8 @@ int pipeline_init() {
 }  // namespace
 
 void pipeline_release() {
+  if (!g_ctx.pipeline) return;
+  struct Drop { ~Drop() { delete static_cast<Pipeline*>(g_ctx.pipeline); g_ctx.pipeline = nullptr; } } drop;
   if (!P.made) return;
   for (auto& s : P.st) {
     DevBuf* all[] = { &s.t, &s.rx, &s.ry, &s.h, &s.yaw, &s.q, &s.x, &s.y, &s.ranges, &s.grids };
@@ -60,7 +69,6 @@ void pipeline_release() {
   cudaStreamDestroy(P.s_out);
   cudaStreamDestroy(P.s_cmp[0]);
   cudaStreamDestroy(P.s_cmp[1]);
-  P = Pipeline();
 }
 
 // flow != nullptr: P0 from flow samples (t_ms, rate_x, rate_y, h, q) then replay; else poses x,y given.
@@ -71,8 +79,23 @@ struct HostLogs {
   float *pox, *poy;                                                     // optional pose output (flow form)
 };
 
+static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames, const HostLogs& L,
+                             int8_t* grids_out, uqs_stats* stats);
+
 int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames, const HostLogs& L,
                   int8_t* grids_out, uqs_stats* stats) {
+  const int rc = host_pipeline_run(p, dp, n_flights, n_frames, L, grids_out, stats);
+  g_ctx.chip_shared = false;
+  if (rc && P.made) {
+    // an early return must not leave copies from / into the caller's buffers in flight
+    for (cudaStream_t s : { P.s_in, P.s_cmp[0], P.s_cmp[1], P.s_out }) cudaStreamSynchronize(s);
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames, const HostLogs& L,
+                             int8_t* grids_out, uqs_stats* stats) {
   int rc = pipeline_init();
   if (rc) return rc;
   const bool flow = L.t_ms != nullptr;
@@ -86,8 +109,9 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
     const int sm = g_ctx.sm_count;
     int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 2 * sm;
     const size_t stage_budget = (size_t)6 << 30;                          // bound the staging buffers (kStages x chunk)
-    if ((size_t)chunk_cap * n_frames * 152 * kStages > stage_budget)
-      chunk_cap = std::max<int>(1, (int)(stage_budget / ((size_t)n_frames * 152 * kStages)));
+    const size_t per_flight = (size_t)n_frames * 152 + cells;             // log bytes + the flight's grid
+    if ((size_t)chunk_cap * per_flight * kStages > stage_budget)
+      chunk_cap = std::max<int>(1, (int)(stage_budget / (per_flight * kStages)));
     if (g_ctx.host_chunk == 0 && chunk_cap == 2 * sm && n_flights >= 8 * sm) {
       starts.push_back(0);
       const int body = n_flights - 2 * sm, n_mid = (body + chunk_cap - 1) / chunk_cap;
@@ -100,6 +124,7 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
     starts.push_back(n_flights);
   }
   const int n_chunks = (int)starts.size() - 1;
+  g_ctx.chip_shared = n_chunks > 1;             // engine and warps-per-CTA choice: neighbours fill the chip
   int chunk = 0;                                // largest chunk: size of the staging buffers
   for (int c = 0; c < n_chunks; c++) chunk = std::max(chunk, starts[c + 1] - starts[c]);
   cudaError_t e = cudaSuccess;

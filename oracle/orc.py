@@ -48,6 +48,8 @@ class Oracle:
         L.orc_beam_cells.restype = None
         L.orc_pose_integrate.argtypes = [C.c_long] + [C.c_void_p] * 8
         L.orc_pose_integrate.restype = None
+        L.orc_pose_integrate_f64.argtypes = [C.c_long] + [C.c_void_p] * 8
+        L.orc_pose_integrate_f64.restype = None
         L.orc_sincosf_sweep.restype = C.c_long
         L.orc_sincosf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
         L.orc_libm_sincosf.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -141,6 +143,16 @@ class Oracle:
             self.L.orc_pose_integrate(N, _vp(t_ms[f]), _vp(rx[f]), _vp(ry[f]), _vp(h[f]), _vp(yaw_deg[f]), _vp(q[f]),
                                       _vp(xo[f]), _vp(yo[f]))
         return (xo[0], yo[0]) if flat else (xo, yo)
+
+    def pose_integrate_f64(self, t_ms, rx, ry, h, yaw_deg, q):
+        """The binary32 increments of the P0 spec accumulated in binary64 (one log): yardstick for the scan variant."""
+        t_ms = np.ascontiguousarray(t_ms, np.uint32).ravel()
+        N = t_ms.size
+        rx, ry, h, yaw_deg = (np.ascontiguousarray(a, np.float32).ravel() for a in (rx, ry, h, yaw_deg))
+        q = np.ascontiguousarray(q, np.uint8).ravel()
+        xo, yo = np.empty(N, np.float64), np.empty(N, np.float64)
+        self.L.orc_pose_integrate_f64(N, _vp(t_ms), _vp(rx), _vp(ry), _vp(h), _vp(yaw_deg), _vp(q), _vp(xo), _vp(yo))
+        return xo, yo
 
     # --- arithmetic KATs --------------------------------------------------------------------
     def libm_sincosf(self, a):

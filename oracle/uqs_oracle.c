@@ -285,6 +285,37 @@ void orc_pose_integrate(long n, const uint32_t* t_ms, const float* rate_x, const
   }
 }
 
+/* The same binary32 increments summed in binary64: the yardstick for the look-back scan variant (mode 1),
+ * which cannot be bit-identical to the binary32 serial sum. */
+void orc_pose_integrate_f64(long n, const uint32_t* t_ms, const float* rate_x, const float* rate_y,
+                            const float* h_m, const float* yaw_deg, const uint8_t* q,
+                            double* xo, double* yo) {
+  if (n <= 0) return;
+  double px = 0.0, py = 0.0;
+  xo[0] = 0.0;
+  yo[0] = 0.0;
+  for (long i = 1; i < n; i++) {
+    float dt = (float)(t_ms[i] - t_ms[i - 1]) * 0.001f;
+    float inc_n = 0.0f, inc_e = 0.0f;
+    if (q[i] >= 50 && !isnan(rate_x[i]) && !isnan(rate_y[i]) && !isnan(h_m[i]) &&
+        !isnan(yaw_deg[i])) {
+      float vbx = rate_x[i] * h_m[i];
+      float vby = rate_y[i] * h_m[i];
+      float a = yaw_deg[i] * ((float)M_PI / 180.0f);
+      float sn, cs;
+      sincosf(a, &sn, &cs);
+      float vn = vbx * cs - vby * sn;
+      float ve = vbx * sn + vby * cs;
+      inc_n = vn * dt;
+      inc_e = ve * dt;
+    }
+    px += (double)inc_n;
+    py += (double)inc_e;
+    xo[i] = px;
+    yo[i] = py;
+  }
+}
+
 /* ------------------------------------------------------------------ */
 /* glibc 2.39 sincosf (FMA build) restated -- SURVEY.md Appendix B       */
 /* ------------------------------------------------------------------ */
@@ -300,12 +331,49 @@ static const double SC_HPI = 0x1.921fb54442d18p+0;      /* pi/2 */
 
 static inline uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-/* returns 1 when |y| is inside the two branches restated here (|y| < 120), else 0 */
+/* 2/pi as a bit string, 24 overlapping 32-bit windows (glibc __inv_pio4) and pi/2 * 2^-62: the
+ * |y| >= 120 branch (reduce_large) multiplies the 24-bit mantissa by 96 bits of 2/pi in integers. */
+static const uint32_t SC_INV_PIO4[24] = {
+  0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27,
+  0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62, 0xc0db6295,
+  0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041 };
+static const double SC_PI63 = 0x1.921FB54442D18p-62;
+
+/* returns 1 for every finite y (all three branches of glibc's sincosf are restated); Inf/NaN give NaN, NaN
+ * like libm and return 1 as well -- the return value is kept for callers written against the earlier form */
 int orc_sincosf_restated(float y, float* sinp, float* cosp) {
   const uint32_t top12 = (f32_bits(y) >> 20) & 0x7ff;
   double x = (double)y, xs, x2;
   const orc_sc_poly* p = &SC_POS;
   int n = 0;
+  if (top12 >= 0x42f) {
+    if (top12 >= 0x7f8) {              /* Inf, NaN: y - y */
+      *sinp = *cosp = y - y;
+      return 1;
+    }
+    /* |y| >= 120: reduce_large */
+    uint32_t xi = f32_bits(y);
+    const int sign = (int)(xi >> 31);
+    const uint32_t* arr = &SC_INV_PIO4[(xi >> 26) & 15];
+    const int shift = (xi >> 23) & 7;
+    uint64_t res0, res1, res2, nn;
+    xi = (xi & 0xffffff) | 0x800000;
+    xi <<= shift;
+    res0 = (uint32_t)(xi * arr[0]);
+    res1 = (uint64_t)xi * arr[4];
+    res2 = (uint64_t)xi * arr[8];
+    res0 = (res2 >> 32) | (res0 << 32);
+    res0 += res1;
+    nn = (res0 + (1ULL << 61)) >> 62;
+    res0 -= nn << 62;
+    x = (double)(int64_t)res0 * SC_PI63;
+    n = (int)nn;
+    static const double sgn4[4] = { 1.0, -1.0, -1.0, 1.0 };
+    xs = x * sgn4[(n + sign) & 3];
+    x2 = x * x;
+    if ((n + sign) & 2) p = &SC_NEG;
+    goto poly;
+  }
   if (top12 < 0x3f4) {                 /* |y| < pi/4 */
     if (top12 < 0x398) {               /* |y| < 2^-12 */
       *sinp = y;
@@ -314,7 +382,7 @@ int orc_sincosf_restated(float y, float* sinp, float* cosp) {
     }
     x2 = x * x;
     xs = x;
-  } else if (top12 < 0x42f) {          /* |y| < 120 */
+  } else {                             /* |y| < 120 */
     double r = x * SC_HPI_INV;
     n = ((int32_t)r + 0x800000) >> 24;
     x = fma(-(double)n, SC_HPI, x);    /* one rounding */
@@ -322,9 +390,8 @@ int orc_sincosf_restated(float y, float* sinp, float* cosp) {
     xs = x * sgn[n & 3];
     x2 = x * x;
     if (n & 2) p = &SC_NEG;
-  } else {
-    return 0;
   }
+poly:;
   double x3 = x2 * xs, x4 = x2 * x2;
   double s1 = fma(x2, p->s3, p->s2);
   double c2 = fma(x2, p->c4, p->c3);

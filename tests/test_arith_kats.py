@@ -30,10 +30,13 @@ def test_saturating_updates_do_not_commute():
 
 
 def test_sincosf_restatement_equals_glibc_exhaustive(oracle):
-    """every float with |y| < 120 (2.24 G values incl. sign): restated glibc-2.39 sincosf == libm sincosf."""
+    """EVERY float (4.29 G bit patterns: |y| < 120, glibc's reduce_large branch above that, Inf and all NaNs):
+    restated glibc-2.39 sincosf == libm sincosf, bit for bit."""
     threads = min(os.cpu_count() or 1, 64)
     bad, first = oracle.sincosf_sweep(0, 0x42F00000, 1, threads)
-    assert bad == 0, f"{bad} mismatches, first at bits {first:#x}"
+    assert bad == 0, f"|y| < 120: {bad} mismatches, first at bits {first:#x}"
+    bad, first = oracle.sincosf_sweep(0x42F00000, 0x80000000, 1, threads)
+    assert bad == 0, f"|y| >= 120 / Inf / NaN: {bad} mismatches, first at bits {first:#x}"
 
 
 def test_glibc_sincosf_is_not_correctly_rounded(oracle):

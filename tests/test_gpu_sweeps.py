@@ -1,5 +1,5 @@
-"""Exhaustive device-vs-host sweep of the restated glibc sincosf (SURVEY Appendix B acceptance test): every float
-with |y| < 120, both signs (2 246 049 792 values; 24 s on the 16-core box).  UQS_SKIP_EXHAUSTIVE=1 skips it; the strided +
+"""Exhaustive device-vs-host sweep of the restated glibc sincosf (SURVEY Appendix B acceptance test): EVERY float
+bit pattern, both signs (4 294 967 296 values: |y| < 120, the reduce_large branch above it, Inf, every NaN).  UQS_SKIP_EXHAUSTIVE=1 skips it; the strided +
 boundary version in test_gpu_parity.py runs always.  Last full run: profiles/r1_sincosf_exhaustive.log."""
 import os
 from concurrent.futures import ThreadPoolExecutor
@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.slow
 @pytest.mark.skipif(os.environ.get("UQS_SKIP_EXHAUSTIVE") == "1", reason="UQS_SKIP_EXHAUSTIVE=1")
 def test_device_sincosf_exhaustive(gpu, oracle):
-    hi = 0x42F00000                      # bits of 120.0f
+    hi = 0x80000000                      # every non-negative bit pattern (120.0f = 0x42F00000, Inf = 0x7F800000)
     chunk = 1 << 25
     threads = min(os.cpu_count() or 1, 32)
     bad = 0
