@@ -187,6 +187,32 @@ int uqs_replay_flow(const uqs_params* p, int n_flights, int n_samples,
                     const float* ranges, int8_t* grids_out,
                     float* poses_out_x, float* poses_out_y, uqs_stats* stats);
 
+/* uqs_replay_flow with the ranges as u16 MILLIMETRES (0xFFFF = no return): the unit the ToF sensors deliver and
+ * the reference converts with `(float)mm * 0.001f` (uav_local_nav.c:1327-1328); the device applies that same
+ * binary32 multiply, so a log given in either form yields identical bytes.  Halves the host-to-device traffic. */
+int uqs_replay_flow_mm(const uqs_params* p, int n_flights, int n_samples,
+                       const uint32_t* t_ms, const float* of_rate_x, const float* of_rate_y,
+                       const float* h_m, const float* yaw_deg, const uint8_t* of_q,
+                       const uint16_t* ranges_mm, int8_t* grids_out,
+                       float* poses_out_x, float* poses_out_y, uqs_stats* stats);
+
+/* uqs_replay_flow with BOXED output: per flight the bounding box of every cell it touched
+ * (boxes_out[f] = {x0, y0, x1, y1}, upper corner exclusive; all zeros for a flight without any accepted ray) and
+ * the box's cells, row-major with row pitch x1 - x0, at packed_out + offsets_out[f].  Cells outside the box are 0
+ * by construction (uav_local_nav.c:2190 and no update reached them).  Exactly one of ranges (float metres) /
+ * ranges_mm (u16 millimetres) is non-NULL.  packed_cap = bytes available at packed_out (n_flights * W * H always
+ * suffices); *packed_bytes = bytes used; UQS_ERR_NOMEM when more were needed.  The device-to-host traffic is the
+ * touched region only (~28 % of a 400x400 grid for a 60 s flight).  uqs_unpack_boxed() (plain host code) expands
+ * the result to dense [n_flights][H][W] grids. */
+int uqs_replay_flow_boxed(const uqs_params* p, int n_flights, int n_samples,
+                          const uint32_t* t_ms, const float* of_rate_x, const float* of_rate_y,
+                          const float* h_m, const float* yaw_deg, const uint8_t* of_q,
+                          const float* ranges, const uint16_t* ranges_mm,
+                          int32_t* boxes_out, uint64_t* offsets_out, int8_t* packed_out, size_t packed_cap,
+                          size_t* packed_bytes, float* poses_out_x, float* poses_out_y, uqs_stats* stats);
+int uqs_unpack_boxed(const uqs_params* p, int n_flights, const int32_t* boxes, const uint64_t* offsets,
+                     const int8_t* packed, int8_t* grids_out);
+
 /* Device-pointer form of uqs_pose_integrate (asynchronous on the current stream). */
 int uqs_pose_integrate_dev(int n_flights, int n_samples,
                            const uint32_t* t_ms, const float* of_rate_x, const float* of_rate_y,
@@ -296,6 +322,16 @@ void uqs_multi_shutdown(void);
 int  uqs_multi_replay_banded(const uqs_params* p, int n_frames, const float* x, const float* y,
                              const float* yaw_deg, const float* ranges, int8_t* grid_out, uqs_stats* stats);
 const int8_t* uqs_multi_grid_dev(int i);   /* device i's copy of the whole grid after the call above */
+
+/* Order-independent 64-bit digest of a grid: sum over cells i of splitmix64(i << 8 | (uint8)cell) mod 2^64.
+ * Lets harnesses compare grids across GPUs / GPU counts without moving them.  _dev: n_grids device grids of
+ * `cells` bytes each -> hashes_out[n_grids] (host), synchronises; uqs_grid_hash: one host grid, host arithmetic. */
+int      uqs_grid_hashes_dev(const int8_t* grids_dev, int n_grids, size_t cells, uint64_t* hashes_out);
+uint64_t uqs_grid_hash(const int8_t* grid, size_t cells);
+
+/* Measurement knob: != 0 makes the host-buffer calls (uqs_replay, uqs_replay_flow[_mm]) run their copies and
+ * synchronisation only, no kernels -- the copy floor bench.py reports beside the end-to-end time. */
+int uqs_set_copy_only(int on);
 
 /* Measured on-chip read-modify-write ceiling: every warp of a full grid does
  * conflict-free byte RMWs on its shared-memory sub-tile.  Returns updates/s. */

@@ -90,6 +90,7 @@ _EXPORTS = [
     "uqs_flight_shard", "uqs_row_band", "uqs_comm_unique_id", "uqs_comm_init_rank", "uqs_comm_destroy", "uqs_comm_nranks",
     "uqs_comm_rank", "uqs_nccl_version", "uqs_replay_banded_dev", "uqs_replay_banded", "uqs_multi_init", "uqs_multi_count",
     "uqs_multi_select", "uqs_multi_shutdown", "uqs_multi_replay_banded", "uqs_multi_grid_dev",
+    "uqs_grid_hashes_dev", "uqs_grid_hash", "uqs_set_copy_only", "uqs_replay_flow_mm", "uqs_replay_flow_boxed", "uqs_unpack_boxed",
     # drop-in symbols
     "uqs_dropin_configure", "uqs_dropin_flush", "uqs_dropin_upload", "map_reset",
     "occ_grid", "map_inited", "map_origin_x", "map_origin_y", "tof_beams_m", "pending_kf_flags",
@@ -152,6 +153,13 @@ def lib() -> C.CDLL:
     L.uqs_multi_replay_banded.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, C.POINTER(Stats)]
     L.uqs_multi_grid_dev.argtypes = [ip]
     L.uqs_multi_grid_dev.restype = C.c_void_p
+    L.uqs_replay_flow_mm.argtypes = [C.POINTER(Params), ip, ip] + [vp] * 10 + [C.POINTER(Stats)]
+    L.uqs_replay_flow_boxed.argtypes = [C.POINTER(Params), ip, ip] + [vp] * 11 + [C.c_size_t, C.POINTER(C.c_size_t), vp, vp, C.POINTER(Stats)]
+    L.uqs_unpack_boxed.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp]
+    L.uqs_grid_hashes_dev.argtypes = [vp, ip, C.c_size_t, vp]
+    L.uqs_grid_hash.argtypes = [vp, C.c_size_t]
+    L.uqs_grid_hash.restype = C.c_uint64
+    L.uqs_set_copy_only.argtypes = [ip]
     L.map_recenter_shift.argtypes = [ip, ip]
     L.map_recenter_shift.restype = None
     L.map_recentre_if_needed.argtypes = [C.c_float, C.c_float]
@@ -278,6 +286,57 @@ def replay_flow(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, range
                                  _ptr(ranges), _ptr(grids), _ptr(px) if want_poses else None,
                                  _ptr(py) if want_poses else None, C.byref(st)))
     return grids, px, py, st.as_dict()
+
+
+def _flow_args(t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q):
+    t_ms = np.ascontiguousarray(t_ms, dtype=np.uint32)
+    if t_ms.ndim == 1:
+        t_ms = t_ms[None]
+    F, N = t_ms.shape
+    rx, ry, h, yaw = (_f32(a).reshape(F, N) for a in (of_rate_x, of_rate_y, h_m, yaw_deg))
+    q = np.ascontiguousarray(of_q, dtype=np.uint8).reshape(F, N)
+    return F, N, t_ms, rx, ry, h, yaw, q
+
+
+def replay_flow_mm(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, ranges_mm, want_poses=True,
+                   out: Optional[np.ndarray] = None):
+    """``uqs_replay_flow_mm``: as replay_flow with ranges as u16 millimetres (0xFFFF = no return)."""
+    F, N, t_ms, rx, ry, h, yaw, q = _flow_args(t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q)
+    mm = np.ascontiguousarray(ranges_mm, dtype=np.uint16).reshape(F, N, BEAMS_PER_FRAME)
+    grids = out if out is not None else np.empty((F, p.H, p.W), np.int8)
+    px = np.empty((F, N), np.float32) if want_poses else None
+    py = np.empty((F, N), np.float32) if want_poses else None
+    st = Stats()
+    _check(lib().uqs_replay_flow_mm(C.byref(p), F, N, _ptr(t_ms), _ptr(rx), _ptr(ry), _ptr(h), _ptr(yaw), _ptr(q), _ptr(mm),
+                                    _ptr(grids), _ptr(px) if want_poses else None, _ptr(py) if want_poses else None, C.byref(st)))
+    return grids, px, py, st.as_dict()
+
+
+def replay_flow_boxed(p: Params, t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, ranges=None, ranges_mm=None,
+                      packed: Optional[np.ndarray] = None, boxes: Optional[np.ndarray] = None, offsets: Optional[np.ndarray] = None):
+    """``uqs_replay_flow_boxed``: returns (boxes [F,4] int32, offsets [F] uint64, packed int8, bytes used, stats)."""
+    F, N, t_ms, rx, ry, h, yaw, q = _flow_args(t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q)
+    if (ranges is None) == (ranges_mm is None):
+        raise ValueError("exactly one of ranges / ranges_mm")
+    r = _f32(ranges).reshape(F, N, BEAMS_PER_FRAME) if ranges is not None else None
+    mm = np.ascontiguousarray(ranges_mm, dtype=np.uint16).reshape(F, N, BEAMS_PER_FRAME) if ranges_mm is not None else None
+    boxes = boxes if boxes is not None else np.empty((F, 4), np.int32)
+    offsets = offsets if offsets is not None else np.empty(F, np.uint64)
+    packed = packed if packed is not None else np.empty(F * p.W * p.H, np.int8)
+    used = C.c_size_t(0)
+    st = Stats()
+    _check(lib().uqs_replay_flow_boxed(C.byref(p), F, N, _ptr(t_ms), _ptr(rx), _ptr(ry), _ptr(h), _ptr(yaw), _ptr(q),
+                                       _ptr(r) if r is not None else None, _ptr(mm) if mm is not None else None,
+                                       _ptr(boxes), _ptr(offsets), _ptr(packed), packed.nbytes, C.byref(used), None, None, C.byref(st)))
+    return boxes, offsets, packed, int(used.value), st.as_dict()
+
+
+def unpack_boxed(p: Params, boxes, offsets, packed, out: Optional[np.ndarray] = None):
+    """``uqs_unpack_boxed``: dense [F,H,W] grids from the boxed form."""
+    F = boxes.shape[0]
+    grids = out if out is not None else np.empty((F, p.H, p.W), np.int8)
+    _check(lib().uqs_unpack_boxed(C.byref(p), F, _ptr(boxes), _ptr(offsets), _ptr(packed), _ptr(grids)))
+    return grids
 
 
 def pose_integrate(t_ms, of_rate_x, of_rate_y, h_m, yaw_deg, of_q, mode: int = 0):
@@ -492,6 +551,23 @@ def multi_replay_banded(p: Params, x, y, yaw_deg, ranges, out: Optional[np.ndarr
     st = Stats()
     _check(lib().uqs_multi_replay_banded(C.byref(p), n, _ptr(x), _ptr(y), _ptr(yaw_deg), _ptr(ranges), _ptr(grid), C.byref(st)))
     return grid, st.as_dict()
+
+
+def grid_hashes_dev(grids_ptr: int, n_grids: int, cells: int) -> np.ndarray:
+    """``uqs_grid_hashes_dev``: 64-bit digest of each device grid (sum of splitmix64(i << 8 | byte)); synchronises."""
+    out = np.empty(n_grids, np.uint64)
+    _check(lib().uqs_grid_hashes_dev(C.c_void_p(grids_ptr), int(n_grids), int(cells), _ptr(out)))
+    return out
+
+
+def grid_hash(grid: np.ndarray) -> int:
+    """``uqs_grid_hash``: the same digest of one host grid (plain host arithmetic in the C library)."""
+    g = np.ascontiguousarray(grid, np.int8)
+    return int(lib().uqs_grid_hash(_ptr(g), g.size))
+
+
+def set_copy_only(on: bool):
+    _check(lib().uqs_set_copy_only(1 if on else 0))
 
 
 def measure_rmw_peak() -> float:

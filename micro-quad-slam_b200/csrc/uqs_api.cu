@@ -103,6 +103,7 @@ int make_dev_params(const uqs_params* p, DevParams* d) {
   }
   d->lo_free = p->lo_free; d->lo_occ = p->lo_occ; d->lo_min = p->lo_min; d->lo_max = p->lo_max;
   d->end_nohit = -(p->lo_free / 2);
+  d->ranges_u16 = 0;
   return UQS_OK;
 }
 
@@ -269,6 +270,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     if (e != cudaSuccess) return cuda_fail(e, "memset stats");
   }
 
+  g_ctx.w->boxes_valid = false;
   int ctas_per_sm = 0;
   e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");
@@ -281,7 +283,9 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     const size_t fo = (size_t)f0 * n_frames;
     KernelTimer t_setup(1);
     k_ray_setup<<<dim3((unsigned)gpf, (unsigned)nf), 1024, 0, st>>>(
-        dp, n_frames, x + fo, y + fo, yaw + fo, ranges + fo * 32, kind ? kind + fo : nullptr, may_reside ? 1 : 0,
+        dp, n_frames, x + fo, y + fo, yaw + fo,
+        dp.ranges_u16 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(ranges) + fo * 32) : ranges + fo * 32,
+        kind ? kind + fo : nullptr, may_reside ? 1 : 0,
         (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
     e = cudaGetLastError();
     t_setup.stop();
@@ -304,6 +308,8 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       if (e != cudaSuccess) return cuda_fail(e, "k_flight_boxes");
       const int dims[2] = { g_ctx.w->h_dims[0], g_ctx.w->h_dims[1] };
       g_ctx.launches += 2;                                     // boxes, publish
+      g_ctx.w->boxes_valid = nf == n_flights;                  // one internal chunk: the boxes describe the whole call
+      g_ctx.w->boxes_n = nf; g_ctx.w->box_w = dims[0]; g_ctx.w->box_h = dims[1];
       const int bw = std::max(dims[0], 4), bh = std::max(dims[1], 1);
       int fpitch = (bw + 3) & ~3;
       if (((fpitch >> 2) & 1) == 0) fpitch += 4;
@@ -481,7 +487,7 @@ int pose_device(int n_flights, int n_samples, const uint32_t* t_ms, const float*
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_pose_increments launch");
   if (mode == 0) {
-    const int warps_per_block = 4;
+    const int warps_per_block = 4;               // kChainWarps of k_pose_chain
     k_pose_chain<<<(unsigned)((n_flights + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
         n_flights, n_samples, inc_n, inc_e, xo, yo);
   } else {

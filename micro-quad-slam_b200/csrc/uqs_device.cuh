@@ -20,7 +20,14 @@ struct DevParams {
   float deg2rad;                          // (float)M_PI / 180.0f                (:299)
   int   lo_free, lo_occ, lo_min, lo_max;
   int   end_nohit;                        // -(lo_free / 2), integer division   (:266)
+  int   ranges_u16;                       // the call's range array is u16 millimetres (0xFFFF = no return) instead
+                                          // of float metres; converted as uav_local_nav.c:1328 does, (float)mm * 0.001f
 };
+
+// range reading b of a frame from either input form
+__device__ __forceinline__ float range_from_mm(unsigned mm) {
+  return mm == 0xFFFFu ? __int_as_float(0x7fc00000) : __fmul_rn((float)mm, 0.001f);
+}
 
 // Ray record, 8 bytes:  w0 = dx[12 signed] | dy[12 signed]<<12 | hit<<24 | valid<<25
 //                       w1 = ceil(2^31 / m), m = max(|dx|,|dy|)  (0 when m == 0)

@@ -33,7 +33,8 @@ k_replay_generic(const __grid_constant__ DevParams p, int n_flights, int n_frame
     bool hit = false;
     int st;
     if (!raw) {
-      st = beam_endpoint(p, px, py, third, ranges[fi * 32 + lane], lane, ex, ey, hit);
+      const float dist = p.ranges_u16 ? range_from_mm(reinterpret_cast<const uint16_t*>(ranges)[fi * 32 + lane]) : ranges[fi * 32 + lane];
+      st = beam_endpoint(p, px, py, third, dist, lane, ex, ey, hit);
     } else {
       st = lane == 0 ? 1 : 0;
       ex = third;
@@ -106,6 +107,35 @@ __global__ void k_range_check(const int8_t* __restrict__ grids, int n_flights, i
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(bad, (unsigned long long)mine);
 }
 
+// Order-independent 64-bit digest of a grid: sum over cells of splitmix64(index << 8 | byte).  Position-sensitive
+// (a zero cell still contributes), trivially parallel, and the same formula in plain C (uqs_grid_hash) and numpy
+// (tests): used to compare grids across GPUs / GPU counts without moving them.
+__host__ __device__ inline unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_hash(const int8_t* __restrict__ grids, size_t cells, unsigned long long* __restrict__ out) {
+  const int8_t* g = grids + (size_t)blockIdx.y * cells;
+  unsigned long long h = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (size_t)gridDim.x * blockDim.x)
+    h += mix64(((unsigned long long)i << 8) | (unsigned long long)(uint8_t)g[i]);
+  for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0 && h) atomicAdd(&out[blockIdx.y], h);
+}
+
+cudaError_t grid_hash_launch(const int8_t* grids, int n_grids, size_t cells, unsigned long long* out, cudaStream_t st) {
+  const unsigned bx = (unsigned)std::min<size_t>(std::max<size_t>((cells + 256 * 16 - 1) / (256 * 16), 1), 1024);
+  for (int g0 = 0; g0 < n_grids; g0 += 65535) {
+    const int ng = std::min(65535, n_grids - g0);
+    k_grid_hash<<<dim3(bx, (unsigned)ng), 256, 0, st>>>(grids + (size_t)g0 * cells, cells, out + g0);
+  }
+  return cudaGetLastError();
+}
+
 static unsigned sweep_blocks(size_t items) {
   return (unsigned)std::min<size_t>(std::max<size_t>((items + 255) / 256, 1), (size_t)148 * 16);
 }
@@ -126,3 +156,32 @@ cudaError_t range_check_launch(const int8_t* grids, int n_flights, int W, int H,
 }
 
 }  // namespace uqs
+
+using namespace uqs;
+
+extern "C" {
+
+/* 64-bit digest of each of n_grids device grids of `cells` bytes -> hashes_out (host).  Synchronises. */
+int uqs_grid_hashes_dev(const int8_t* grids_dev, int n_grids, size_t cells, uint64_t* hashes_out) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (!grids_dev || n_grids <= 0 || !cells || !hashes_out) { set_error("uqs_grid_hashes_dev: bad argument"); return UQS_ERR_BAD_ARG; }
+  cudaStream_t st = g_ctx.stream();
+  if ((rc = g_ctx.in_kind.ensure((size_t)n_grids * 8))) return rc;
+  cudaError_t e = zero_async(g_ctx.in_kind.p, (size_t)n_grids * 8, st);
+  if (e == cudaSuccess) e = grid_hash_launch(grids_dev, n_grids, cells, (unsigned long long*)g_ctx.in_kind.p, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hashes_out, g_ctx.in_kind.p, (size_t)n_grids * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "uqs_grid_hashes_dev");
+  g_ctx.launches += 2 + (n_grids - 1) / 65535;
+  return UQS_OK;
+}
+
+/* the same digest of a host grid, in plain host arithmetic (for harnesses that hold the grid in RAM) */
+uint64_t uqs_grid_hash(const int8_t* grid, size_t cells) {
+  unsigned long long h = 0;
+  for (size_t i = 0; i < cells; i++) h += mix64(((unsigned long long)i << 8) | (unsigned long long)(uint8_t)grid[i]);
+  return h;
+}
+
+}  // extern "C"

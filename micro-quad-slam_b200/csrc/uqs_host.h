@@ -25,6 +25,8 @@ struct Work {
   int order_nsx = 0, order_nsy = 0;             // geometry the cached tile order was built for
   cudaStream_t stream = nullptr;
   int* h_dims = nullptr;                        // mapped host words the box kernel publishes its maxima to
+  bool boxes_valid = false;                     // `boxes` holds the touched boxes of the last replay_device call's
+  int boxes_n = 0, box_w = 0, box_h = 0;        //   boxes_n flights (one internal chunk), maxima box_w x box_h
   void release() {
     if (h_dims) cudaFreeHost(h_dims);
     h_dims = nullptr;
@@ -45,6 +47,7 @@ struct Context {
   int engine = 0;                               // 0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA
   int flight_warps = 0;                         // warps per CTA of the resident engine (0 = 16)
   int host_chunk = 0;                           // flights per chunk of the host-buffer pipeline (0 = auto)
+  bool copy_only = false;                       // measurement: host-buffer calls skip their kernels (uqs_set_copy_only)
   bool chip_shared = false;                     // a multi-chunk host-buffer call is in flight: chunks share the chip
   size_t scratch_budget = (size_t)12 << 30;     // ray/frame records held at once
   unsigned long long launches = 0;              // kernels launched by this library

@@ -55,32 +55,65 @@ __global__ void k_pose_increments(long long total, int n_samples, const uint32_t
   inc_e[i] = de;
 }
 
-// One warp per flight replays the summation in sample order.  Lanes load 32 increments
-// at a time (coalesced); the running sum is carried through a shuffle broadcast so every
-// add happens in exactly the order of the CPU statement.
-__global__ void k_pose_chain(int n_flights, int n_samples, const float* __restrict__ inc_n,
-                             const float* __restrict__ inc_e, float* __restrict__ xo,
-                             float* __restrict__ yo) {
-  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_flights) return;
-  const size_t base = (size_t)warp * n_samples;
-  float px = 0.0f, py = 0.0f;
-  for (int s0 = 0; s0 < n_samples; s0 += 32) {
-    const int s = s0 + lane;
-    const float dn = (s < n_samples) ? inc_n[base + s] : 0.0f;
-    const float de = (s < n_samples) ? inc_e[base + s] : 0.0f;
-    float mx = 0.0f, my = 0.0f;
+// One warp per flight replays the summation in sample order.  The order is fixed by the spec (and by bit-exactness:
+// binary32 addition is not associative), so the sum itself is a serial chain of dependent FADDs -- 4 cycles each --
+// and everything else is arranged so that the chain never waits: the 32 lanes stage 256 increments at a time in
+// shared memory (coalesced loads, issued one chunk ahead so that their latency hides behind the chain of the
+// previous chunk), lane 0 runs the chain over them with vector loads and writes the running sums back in place, and
+// all lanes store the 256 poses coalesced.  x and y are two independent chains interleaved in the same lane.
+// One long log (config 2: 360 000 samples, a single warp on the whole chip): 4.6 ms with the former shuffle
+// broadcast (one global-load latency per 32 samples on the critical path) -> measured value in profiles/.
+constexpr int kChainChunk = 256;              // samples per staged chunk (8 per lane)
+constexpr int kChainWarps = 4;                // warps (= flights) per block
+
+__global__ void __launch_bounds__(kChainWarps * 32)
+k_pose_chain(int n_flights, int n_samples, const float* __restrict__ inc_n,
+             const float* __restrict__ inc_e, float* __restrict__ xo,
+             float* __restrict__ yo) {
+  __shared__ __align__(16) float s_n[kChainWarps][kChainChunk], s_e[kChainWarps][kChainChunk];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int flight = blockIdx.x * kChainWarps + wib;
+  if (flight >= n_flights) return;
+  const size_t base = (size_t)flight * n_samples;
+  float* sn = s_n[wib];
+  float* se = s_e[wib];
+  constexpr int PER = kChainChunk / 32;
+  float rn[PER], re[PER];
+  auto fetch = [&](int s0) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      px = __fadd_rn(px, __shfl_sync(0xffffffffu, dn, j));
-      py = __fadd_rn(py, __shfl_sync(0xffffffffu, de, j));
-      if (j == lane) { mx = px; my = py; }
+    for (int u = 0; u < PER; u++) {
+      const int s = s0 + u * 32 + lane;
+      rn[u] = (s < n_samples) ? __ldg(&inc_n[base + s]) : 0.0f;
+      re[u] = (s < n_samples) ? __ldg(&inc_e[base + s]) : 0.0f;
     }
-    if (s < n_samples) {
-      xo[base + s] = mx;
-      yo[base + s] = my;
+  };
+  fetch(0);
+  float px = 0.0f, py = 0.0f;
+  for (int s0 = 0; s0 < n_samples; s0 += kChainChunk) {
+#pragma unroll
+    for (int u = 0; u < PER; u++) { sn[u * 32 + lane] = rn[u]; se[u * 32 + lane] = re[u]; }
+    if (s0 + kChainChunk < n_samples) fetch(s0 + kChainChunk);     // in flight while lane 0 works through this chunk
+    __syncwarp();
+    if (lane == 0) {
+      const int cnt = min(kChainChunk, n_samples - s0);
+      for (int i = 0; i < cnt; i += 4) {                           // padding past the end holds zeros: harmless adds
+        float4 a = *reinterpret_cast<const float4*>(&sn[i]);
+        float4 b = *reinterpret_cast<const float4*>(&se[i]);
+        a.x = px = __fadd_rn(px, a.x); b.x = py = __fadd_rn(py, b.x);
+        a.y = px = __fadd_rn(px, a.y); b.y = py = __fadd_rn(py, b.y);
+        a.z = px = __fadd_rn(px, a.z); b.z = py = __fadd_rn(py, b.z);
+        a.w = px = __fadd_rn(px, a.w); b.w = py = __fadd_rn(py, b.w);
+        *reinterpret_cast<float4*>(&sn[i]) = a;
+        *reinterpret_cast<float4*>(&se[i]) = b;
+      }
     }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int s = s0 + u * 32 + lane;
+      if (s < n_samples) { xo[base + s] = sn[u * 32 + lane]; yo[base + s] = se[u * 32 + lane]; }
+    }
+    __syncwarp();                                                  // the chunk is rewritten next turn
   }
 }
 
@@ -227,14 +260,18 @@ k_ray_setup(const __grid_constant__ DevParams p, int n_frames, const float* __re
   const size_t fbase = (size_t)flight * n_frames;
   const int nfr = min(32, n_frames - g * 32);                     // frames of this block
 
-  // stage the block's range readings: one bulk copy (needs 16-byte alignment; plain loads otherwise)
-  const float* blk_ranges = ranges + (fbase + (size_t)g * 32) * 32;
+  // stage the block's range readings: one bulk copy (needs 16-byte alignment; plain loads otherwise).
+  // The log holds them as float metres (128 B per frame) or as u16 millimetres (64 B per frame).
+  const bool u16 = p.ranges_u16 != 0;
+  const unsigned rbytes = u16 ? 64u : 128u;
+  const unsigned char* ranges_b = reinterpret_cast<const unsigned char*>(ranges);
+  const unsigned char* blk_ranges = ranges_b + (fbase + (size_t)g * 32) * rbytes;
   const bool staged = (reinterpret_cast<size_t>(ranges) & 15) == 0;
   const uint32_t bar_sa = (uint32_t)__cvta_generic_to_shared(&s_bar);
   if (staged) {
     if (threadIdx.x == 0) {
       mbar_init(bar_sa, 1);
-      bulk_load_g2s((uint32_t)__cvta_generic_to_shared(s_rng), blk_ranges, (uint32_t)nfr * 128u, bar_sa);
+      bulk_load_g2s((uint32_t)__cvta_generic_to_shared(s_rng), blk_ranges, (uint32_t)nfr * rbytes, bar_sa);
     }
     __syncthreads();                                               // the barrier object is visible to every waiter
   }
@@ -263,9 +300,11 @@ k_ray_setup(const __grid_constant__ DevParams p, int n_frames, const float* __re
     const float px = x[fi], py = y[fi], third = yaw_deg[fi];
     raw = kind != nullptr && kind[fi] == 1;
     if (staged) mbar_wait(bar_sa, 0);
-    const float* rr = staged ? &s_rng[w * 32] : &ranges[fi * 32];
+    const unsigned char* rb = staged ? reinterpret_cast<const unsigned char*>(s_rng) + (size_t)w * rbytes : ranges_b + fi * rbytes;
+    const float* rr = reinterpret_cast<const float*>(rb);
     if (!raw) {
-      st = beam_endpoint(p, px, py, third, rr[lane], lane, ex, ey, hit);
+      const float dist = u16 ? range_from_mm(reinterpret_cast<const uint16_t*>(rb)[lane]) : rr[lane];
+      st = beam_endpoint(p, px, py, third, dist, lane, ex, ey, hit);
     } else {
       st = (lane == 0) ? 1 : 0;
       ex = third;

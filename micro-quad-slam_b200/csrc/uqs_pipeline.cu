@@ -8,6 +8,7 @@
 // Copies overlap only from page-locked host memory (cudaHostRegister / cudaHostAlloc / torch
 // pin_memory); pageable buffers still work, serialised by the driver.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "uqs_host.h"
@@ -19,7 +20,7 @@ namespace {
 constexpr int kStages = 4;
 
 struct Stage {                 // device staging of one chunk (kStages of them rotate)
-  DevBuf t, rx, ry, h, yaw, q, x, y, ranges, grids;
+  DevBuf t, rx, ry, h, yaw, q, x, y, ranges, grids, packed, boxes;
   cudaEvent_t in_ready = nullptr, computed = nullptr, out_done = nullptr;
 };
 
@@ -59,7 +60,7 @@ void pipeline_release() {
   struct Drop { ~Drop() { delete static_cast<Pipeline*>(g_ctx.pipeline); g_ctx.pipeline = nullptr; } } drop;
   if (!P.made) return;
   for (auto& s : P.st) {
-    DevBuf* all[] = { &s.t, &s.rx, &s.ry, &s.h, &s.yaw, &s.q, &s.x, &s.y, &s.ranges, &s.grids };
+    DevBuf* all[] = { &s.t, &s.rx, &s.ry, &s.h, &s.yaw, &s.q, &s.x, &s.y, &s.ranges, &s.grids, &s.packed, &s.boxes };
     for (DevBuf* b : all) b->release();
     cudaEventDestroy(s.in_ready);
     cudaEventDestroy(s.computed);
@@ -77,7 +78,38 @@ struct HostLogs {
   const float *x, *y;                                                   // pose form
   const float* yaw; const float* ranges;
   float *pox, *poy;                                                     // optional pose output (flow form)
+  const uint16_t* ranges_mm = nullptr;                                  // ranges as u16 millimetres instead of float metres
+  // boxed output (instead of grids_out): per flight its touched box and the box's cells
+  int32_t* boxes_out = nullptr; uint64_t* offsets_out = nullptr; int8_t* packed_out = nullptr;
+  size_t packed_cap = 0; size_t* packed_bytes = nullptr;
 };
+
+// Copies each flight's box [x0,x1) x [y0,y1) of its W x H grid into a slot of `slot` bytes (row pitch x1 - x0).
+__global__ void k_pack_boxes(const int8_t* __restrict__ grids, const int4* __restrict__ boxes, int W, int H, size_t slot,
+                             int8_t* __restrict__ packed) {
+  const int f = blockIdx.x;
+  const int4 b = boxes[f];
+  const int bw = b.z - b.x, bh = b.w - b.y;
+  const int8_t* g = grids + (size_t)f * W * H + (size_t)b.y * W + b.x;
+  int8_t* out = packed + (size_t)f * slot;
+  if (((bw | b.x | W) & 3) == 0) {
+    const int wpr = bw >> 2;
+    for (int i = threadIdx.x; i < wpr * bh; i += blockDim.x) {
+      const int r = i / wpr, c = i - r * wpr;
+      reinterpret_cast<uint32_t*>(out)[i] = reinterpret_cast<const uint32_t*>(g + (size_t)r * W)[c];
+    }
+  } else {
+    for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
+      const int r = i / bw, c = i - r * bw;
+      out[i] = g[(size_t)r * W + c];
+    }
+  }
+}
+
+__global__ void k_whole_boxes(int n, int W, int H, int4* boxes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) boxes[i] = make_int4(0, 0, W, H);
+}
 
 static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames, const HostLogs& L,
                              int8_t* grids_out, uqs_stats* stats);
@@ -94,10 +126,16 @@ int host_pipeline(const uqs_params* p, const DevParams& dp, int n_flights, int n
   return rc;
 }
 
-static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_flights, int n_frames, const HostLogs& L,
+static int host_pipeline_run(const uqs_params* p, const DevParams& dp_in, int n_flights, int n_frames, const HostLogs& L,
                              int8_t* grids_out, uqs_stats* stats) {
   int rc = pipeline_init();
   if (rc) return rc;
+  DevParams dp = dp_in;
+  dp.ranges_u16 = L.ranges_mm ? 1 : 0;
+  const bool boxed = L.boxes_out != nullptr;
+  const size_t rbytes = L.ranges_mm ? 64 : 128;                      // range bytes per frame
+  size_t packed_used = 0;
+  if (L.packed_bytes) *L.packed_bytes = 0;
   const bool flow = L.t_ms != nullptr;
   const size_t cells = (size_t)p->W * p->H;
   // Chunk schedule: chunks of 2 flights per SM between a first and a last chunk of 1 per SM (the first chunk's H2D and
@@ -109,7 +147,7 @@ static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_fli
     const int sm = g_ctx.sm_count;
     int chunk_cap = g_ctx.host_chunk > 0 ? g_ctx.host_chunk : 2 * sm;
     const size_t stage_budget = (size_t)6 << 30;                          // bound the staging buffers (kStages x chunk)
-    const size_t per_flight = (size_t)n_frames * 152 + cells;             // log bytes + the flight's grid
+    const size_t per_flight = (size_t)n_frames * (24 + rbytes) + cells * (boxed ? 2 : 1);     // log bytes + the flight's grid(s)
     if ((size_t)chunk_cap * per_flight * kStages > stage_budget)
       chunk_cap = std::max<int>(1, (int)(stage_budget / (per_flight * kStages)));
     if (g_ctx.host_chunk == 0 && chunk_cap == 2 * sm && n_flights >= 8 * sm) {
@@ -166,7 +204,8 @@ static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_fli
       cp(S.x, L.x + o, n * 4); cp(S.y, L.y + o, n * 4);
     }
     cp(S.yaw, L.yaw + o, n * 4);
-    cp(S.ranges, L.ranges + o * 32, n * 128);
+    if (L.ranges_mm) cp(S.ranges, L.ranges_mm + o * 32, n * 64);
+    else cp(S.ranges, L.ranges + o * 32, n * 128);
     t_in.stop();
     if (r == cudaSuccess) r = cudaEventRecord(S.in_ready, P.s_in);
     return r;
@@ -185,18 +224,63 @@ static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_fli
     cudaStream_t sc = P.s_cmp[c & 1];
     if ((e = cudaStreamWaitEvent(sc, S.in_ready, 0)) != cudaSuccess) return cuda_fail(e, "wait H2D");
     if (c >= kStages && (e = cudaStreamWaitEvent(sc, S.out_done, 0)) != cudaSuccess) return cuda_fail(e, "wait D2H");   // grid buffer free
-    if (flow) {
+    if (g_ctx.copy_only) {
+      // copies and their ordering only
+    } else if (flow) {
       if ((rc = pose_device(nf, n_frames, (uint32_t*)S.t.p, (float*)S.rx.p, (float*)S.ry.p, (float*)S.h.p, (float*)S.yaw.p,
                             (uint8_t*)S.q.p, (float*)S.x.p, (float*)S.y.p, 0)))
         return rc;
     }
-    if ((rc = replay_device(dp, nf, n_frames, (float*)S.x.p, (float*)S.y.p, (float*)S.yaw.p, (float*)S.ranges.p, nullptr,
+    if (!g_ctx.copy_only &&
+        (rc = replay_device(dp, nf, n_frames, (float*)S.x.p, (float*)S.y.p, (float*)S.yaw.p, (float*)S.ranges.p, nullptr,
                             (int8_t*)S.grids.p, 0, 0, p->H, c < 2)))
       return rc;
+    size_t slot = 0, out_at = 0;
+    if (boxed && !g_ctx.copy_only) {
+      // The chunk's touched boxes (k_flight_boxes ran inside replay_device when the resident engine was a candidate; its
+      // maxima came back through mapped memory before the replay was launched) -> one slot of max_w x max_h bytes per
+      // flight, so the size of the D2H is known here without another synchronisation.
+      const Work& wk = *g_ctx.w;
+      if ((rc = S.boxes.ensure((size_t)nf * sizeof(int4)))) return rc;
+      int4* bx = (int4*)S.boxes.p;
+      if (wk.boxes_valid && wk.boxes_n == nf) {
+        slot = (size_t)std::max(wk.box_w, 1) * std::max(wk.box_h, 1);
+        e = cudaMemcpyAsync(bx, wk.boxes.p, (size_t)nf * sizeof(int4), cudaMemcpyDeviceToDevice, sc);
+      } else {
+        slot = cells;
+        k_whole_boxes<<<(unsigned)((nf + 127) / 128), 128, 0, sc>>>(nf, p->W, p->H, bx);
+        e = cudaGetLastError();
+        g_ctx.launches += 1;
+      }
+      slot = (slot + 15) & ~(size_t)15;
+      if (e == cudaSuccess && (rc = S.packed.ensure((size_t)nf * slot))) return rc;
+      if (e == cudaSuccess) {
+        k_pack_boxes<<<(unsigned)nf, 256, 0, sc>>>((const int8_t*)S.grids.p, bx, p->W, p->H, slot, (int8_t*)S.packed.p);
+        e = cudaGetLastError();
+        g_ctx.launches += 1;
+      }
+      if (e != cudaSuccess) return cuda_fail(e, "k_pack_boxes");
+      out_at = packed_used;
+      packed_used += (size_t)nf * slot;
+      if (L.packed_bytes) *L.packed_bytes = packed_used;
+      if (packed_used > L.packed_cap) {
+        set_error("boxed output needs more than the %zu bytes given (%zu so far at flight %d of %d)", L.packed_cap, packed_used, f0 + nf, n_flights);
+        return UQS_ERR_NOMEM;
+      }
+      for (int i = 0; i < nf; i++) L.offsets_out[f0 + i] = out_at + (size_t)i * slot;
+    }
     if ((e = cudaEventRecord(S.computed, sc)) != cudaSuccess) return cuda_fail(e, "record");
     if ((e = cudaStreamWaitEvent(P.s_out, S.computed, 0)) != cudaSuccess) return cuda_fail(e, "wait compute");
     KernelTimer t_out(4, P.s_out);
-    e = cudaMemcpyAsync(grids_out + (size_t)f0 * cells, S.grids.p, (size_t)nf * cells, cudaMemcpyDeviceToHost, P.s_out);
+    if (boxed) {
+      e = cudaSuccess;
+      if (!g_ctx.copy_only) {
+        e = cudaMemcpyAsync(L.packed_out + out_at, S.packed.p, (size_t)nf * slot, cudaMemcpyDeviceToHost, P.s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(L.boxes_out + (size_t)f0 * 4, S.boxes.p, (size_t)nf * sizeof(int4), cudaMemcpyDeviceToHost, P.s_out);
+      }
+    } else {
+      e = cudaMemcpyAsync(grids_out + (size_t)f0 * cells, S.grids.p, (size_t)nf * cells, cudaMemcpyDeviceToHost, P.s_out);
+    }
     if (e == cudaSuccess && flow && L.pox && L.poy) {
       e = cudaMemcpyAsync(L.pox + o, S.x.p, n * 4, cudaMemcpyDeviceToHost, P.s_out);
       if (e == cudaSuccess) e = cudaMemcpyAsync(L.poy + o, S.y.p, n * 4, cudaMemcpyDeviceToHost, P.s_out);
@@ -208,6 +292,7 @@ static int host_pipeline_run(const uqs_params* p, const DevParams& dp, int n_fli
   // the call is synchronous: results are in the caller's buffers when it returns
   if ((e = cudaStreamSynchronize(P.s_out)) != cudaSuccess) return cuda_fail(e, "D2H sync");
   if ((e = cudaStreamSynchronize(P.s_in)) != cudaSuccess) return cuda_fail(e, "H2D sync");
+  if (g_ctx.copy_only) return UQS_OK;
   uqs_stats local;
   return fetch_stats_mask(stats ? stats : &local, (uint64_t)n_flights * n_frames, n_chunks > 1 ? 6u : 2u);
 }
@@ -246,6 +331,77 @@ int uqs_replay_flow(const uqs_params* p, int n_flights, int n_samples, const uin
   }
   HostLogs L = { t_ms, rx, ry, h, q, nullptr, nullptr, yaw, ranges, pox, poy };
   return host_pipeline(p, dp, n_flights, n_samples, L, grids_out, stats);
+}
+
+/* uqs_replay_flow with the ranges as u16 millimetres (0xFFFF = no return), the unit the ToF sensors deliver
+ * (uav_local_nav.c:1327-1328): converted on the device with the reference's own (float)mm * 0.001f.  Halves the
+ * host-to-device traffic of a log. */
+int uqs_replay_flow_mm(const uqs_params* p, int n_flights, int n_samples, const uint32_t* t_ms,
+                       const float* rx, const float* ry, const float* h, const float* yaw,
+                       const uint8_t* q, const uint16_t* ranges_mm, int8_t* grids_out, float* pox, float* poy,
+                       uqs_stats* stats) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_flights <= 0 || n_samples <= 0 || !t_ms || !rx || !ry || !h || !yaw || !q || !ranges_mm || !grids_out) {
+    set_error("uqs_replay_flow_mm: NULL pointer or non-positive size");
+    return UQS_ERR_BAD_ARG;
+  }
+  HostLogs L = { t_ms, rx, ry, h, q, nullptr, nullptr, yaw, nullptr, pox, poy };
+  L.ranges_mm = ranges_mm;
+  return host_pipeline(p, dp, n_flights, n_samples, L, grids_out, stats);
+}
+
+/* uqs_replay_flow with BOXED output: instead of n_flights dense W x H grids the call returns, per flight, the
+ * bounding box of every cell the flight touched (boxes_out[f] = x0, y0, x1, y1, exclusive upper corner) and the
+ * box's cells, row-major with row pitch x1 - x0, at packed_out + offsets_out[f].  Every cell outside the box is 0
+ * (uav_local_nav.c:2190 and no update).  ranges (float metres) or ranges_mm (u16 millimetres): exactly one non-NULL.
+ * packed_cap = bytes available at packed_out (n_flights * W * H always suffices); *packed_bytes = bytes used
+ * (UQS_ERR_NOMEM if more were needed).  uqs_unpack_boxed() expands the result to dense grids. */
+int uqs_replay_flow_boxed(const uqs_params* p, int n_flights, int n_samples, const uint32_t* t_ms,
+                          const float* rx, const float* ry, const float* h, const float* yaw, const uint8_t* q,
+                          const float* ranges, const uint16_t* ranges_mm, int32_t* boxes_out, uint64_t* offsets_out,
+                          int8_t* packed_out, size_t packed_cap, size_t* packed_bytes, float* pox, float* poy,
+                          uqs_stats* stats) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_flights <= 0 || n_samples <= 0 || !t_ms || !rx || !ry || !h || !yaw || !q || (!ranges == !ranges_mm) || !boxes_out ||
+      !offsets_out || !packed_out) {
+    set_error("uqs_replay_flow_boxed: NULL pointer, non-positive size, or not exactly one of ranges / ranges_mm");
+    return UQS_ERR_BAD_ARG;
+  }
+  HostLogs L = { t_ms, rx, ry, h, q, nullptr, nullptr, yaw, ranges, pox, poy };
+  L.ranges_mm = ranges_mm;
+  L.boxes_out = boxes_out; L.offsets_out = offsets_out; L.packed_out = packed_out;
+  L.packed_cap = packed_cap; L.packed_bytes = packed_bytes;
+  return host_pipeline(p, dp, n_flights, n_samples, L, nullptr, stats);
+}
+
+/* Host helper: dense grids [n_flights][H][W] from the boxed form (plain host code). */
+int uqs_unpack_boxed(const uqs_params* p, int n_flights, const int32_t* boxes, const uint64_t* offsets,
+                     const int8_t* packed, int8_t* grids_out) {
+  if (!p || n_flights <= 0 || !boxes || !offsets || !packed || !grids_out) { set_error("uqs_unpack_boxed: bad argument"); return UQS_ERR_BAD_ARG; }
+  const size_t cells = (size_t)p->W * p->H;
+  memset(grids_out, 0, cells * (size_t)n_flights);
+  for (int f = 0; f < n_flights; f++) {
+    const int32_t* b = boxes + (size_t)f * 4;
+    const int bw = b[2] - b[0], bh = b[3] - b[1];
+    if (bw <= 0 || bh <= 0) continue;
+    if (b[0] < 0 || b[1] < 0 || b[2] > p->W || b[3] > p->H) { set_error("uqs_unpack_boxed: box %d outside the grid", f); return UQS_ERR_BAD_ARG; }
+    for (int r = 0; r < bh; r++)
+      memcpy(grids_out + (size_t)f * cells + (size_t)(b[1] + r) * p->W + b[0], packed + offsets[f] + (size_t)r * bw, (size_t)bw);
+  }
+  return UQS_OK;
+}
+
+int uqs_set_copy_only(int on) {
+  int rc = check_ready();
+  if (rc) return rc;
+  g_ctx.copy_only = on != 0;
+  return UQS_OK;
 }
 
 /* Flights per chunk of the host-buffer pipeline (0 = automatic). */

@@ -49,6 +49,8 @@ typedef struct uqs_synth_cfg {
   float    p_dropout, p_lowq;
   float    h_m;             /* flight height, 0.5 m                                  */
   int32_t  shared_truth;    /* 1: all flights fly the same true trajectory (drift ensemble) */
+  int32_t  range_mm;        /* 1: ranges lie on the sensor's 1 mm lattice: (float)mm * 0.001f, the value the
+                               reference derives from the raw u16 reading (uav_local_nav.c:1328) */
 } uqs_synth_cfg;
 
 typedef struct { uint64_t s; } rng_t;
@@ -185,6 +187,12 @@ static void gen_flight(const synth_job* J, int fl) {
       float v = truth[k] + c->sigma_r * rng_gauss(&r);
       if (v < 0.02f) v = 0.02f;
       if (v > c->max_range_m) v = c->max_range_m;
+      if (c->range_mm) {
+        long mm = lrintf(v * 1000.0f);
+        if (mm < 0) mm = 0;
+        if (mm > 65534) mm = 65534;
+        v = (float)mm * 0.001f;
+      }
       if (rng_uniform(&r) < c->p_dropout) v = NAN;
       out[k] = v;
     }

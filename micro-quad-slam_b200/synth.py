@@ -25,6 +25,7 @@ class SynthCfg(C.Structure):
         ("speed_mps", C.c_float), ("line_spacing_m", C.c_float), ("yaw_rate_dps", C.c_float),
         ("max_range_m", C.c_float), ("sigma_r", C.c_float), ("sigma_f", C.c_float), ("sigma_b", C.c_float),
         ("p_dropout", C.c_float), ("p_lowq", C.c_float), ("h_m", C.c_float), ("shared_truth", C.c_int32),
+        ("range_mm", C.c_int32),
     ]
 
 
@@ -49,6 +50,7 @@ class Workload:
     sigma_f: float = 0.02
     sigma_b: float = 0.005
     shared_truth: int = 0
+    range_mm: int = 0        # 1: ranges on the sensor's 1 mm lattice, (float)mm * 0.001f (uav_local_nav.c:1328)
 
     @property
     def n_frames(self) -> int:
@@ -66,6 +68,7 @@ class Workload:
         c.speed_mps, c.line_spacing_m, c.yaw_rate_dps = self.speed_mps, self.line_spacing_m, 20.0
         c.max_range_m, c.sigma_r, c.sigma_f, c.sigma_b = 4.0, self.sigma_r, self.sigma_f, self.sigma_b
         c.p_dropout, c.p_lowq, c.h_m, c.shared_truth = 0.02, 0.01, 0.5, self.shared_truth
+        c.range_mm = self.range_mm
         return c
 
 
@@ -155,6 +158,34 @@ def generate(w: Workload, flight_id0: int = 0, n_flights: Optional[int] = None, 
         fy[:, 1::2] = fy[:, 1::2] + np.float32(45.0)      # binary32 add, as a caller of the reference would do
         d["frame_yaw_deg"] = fy
     return d
+
+
+def on_mm_lattice(w: Workload) -> Workload:
+    """The same workload with its ranges on the ToF sensor's millimetre lattice (what a real scan log holds)."""
+    return replace(w, range_mm=1)
+
+
+def ranges_to_mm(ranges: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """u16 millimetre form of ranges generated with ``range_mm=1``: NaN (no return) -> 0xFFFF.  Lossless:
+    ``mm_to_ranges(ranges_to_mm(r))`` reproduces r bit for bit (checked by the caller or the tests)."""
+    r = np.asarray(ranges, np.float32)
+    mm = out if out is not None else np.empty(r.shape, np.uint16)
+    blk = 1 << 24
+    rf, mf = r.reshape(-1), mm.reshape(-1)
+    for a in range(0, rf.size, blk):
+        v = rf[a:a + blk]
+        nan = np.isnan(v)
+        q = np.rint(np.where(nan, np.float32(0), v) * np.float32(1000.0))
+        q[nan] = 65535
+        mf[a:a + blk] = q.astype(np.uint16)
+    return mm
+
+
+def mm_to_ranges(mm: np.ndarray) -> np.ndarray:
+    """(float)mm * 0.001f in binary32, 0xFFFF -> NaN: the conversion the device applies (uav_local_nav.c:1327-1328)."""
+    r = mm.astype(np.float32) * np.float32(0.001)
+    r[mm == 0xFFFF] = np.nan
+    return r
 
 
 def frame_poses(d: dict, x: np.ndarray, y: np.ndarray):

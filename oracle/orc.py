@@ -64,6 +64,8 @@ class Oracle:
         L.orc_frontier_score_dir.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 4
         L.orc_slice_map_check.restype = C.c_long
         L.orc_slice_map_check.argtypes = [C.c_long, C.c_uint64]
+        L.orc_grid_hash64.restype = C.c_uint64
+        L.orc_grid_hash64.argtypes = [C.c_void_p, C.c_size_t]
         L.orc_fnv1a32.restype = C.c_uint32
         L.orc_fnv1a32.argtypes = [C.c_void_p, C.c_size_t]
 
@@ -165,6 +167,11 @@ class Oracle:
         first = C.c_uint32(0)
         bad = self.L.orc_sincosf_sweep(lo_bits, hi_bits, stride, threads, C.byref(first))
         return int(bad), first.value
+
+    def grid_hash64(self, a: np.ndarray) -> int:
+        """sum over cells of splitmix64(i << 8 | byte): the digest the product computes on the device."""
+        a = np.ascontiguousarray(a)
+        return int(self.L.orc_grid_hash64(_vp(a), a.nbytes))
 
     def fnv1a32(self, a: np.ndarray) -> int:
         a = np.ascontiguousarray(a)

@@ -598,6 +598,19 @@ long orc_slice_map_check(long n_seq, uint64_t seed) {
 }
 
 /* FNV-1a over a byte buffer (grid fingerprints in tests and golden files). */
+/* 64-bit digest of a grid, the formula of include/uqs_mapping.h (uqs_grid_hash): sum over cells i of
+ * splitmix64(i << 8 | byte).  Restated here so that the checker does not call the product. */
+uint64_t orc_grid_hash64(const uint8_t* g, size_t n) {
+  uint64_t h = 0;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t z = (((uint64_t)i << 8) | g[i]) + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    h += z ^ (z >> 31);
+  }
+  return h;
+}
+
 uint32_t orc_fnv1a32(const uint8_t* p, size_t n) {
   uint32_t h = 0x811c9dc5u;
   for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 0x01000193u; }

@@ -49,32 +49,38 @@ def main():
         assert np.array_equal(sums.cpu().numpy(), want.reshape(w.n_flights, -1).astype(np.int64).sum(1)), "flight shards differ"
         print(f"[multigpu] flight shards over {world} GPUs: checksums equal the oracle's", flush=True)
 
-    # (b) owned row bands of one 16384^2 grid + one NCCL all-gather ----------------------------------
+    # (b) owned row bands of one 16384^2 grid + one NCCL all-gather, all inside the C library -------------------
+    uid = torch.zeros(m.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(m.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)                       # the launcher's own plumbing carries the 128 bytes
+    m.comm_init_rank(bytes(uid.cpu().numpy().tobytes()), world, rank)
+    assert m.comm_nranks() == world
     n_samples = int(os.environ.get("UQS_C4_SAMPLES", "4000"))
     w4 = synth.scaled(synth.CONFIGS["c4"], n_samples=n_samples)
     p4 = w4.params()
     d4 = synth.generate(w4)                       # every rank sees the whole log
     x, y = synth.frame_poses(d4, d4["x_true"], d4["y_true"])
     tx, ty, tyaw, tr = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x, y, d4["frame_yaw_deg"], d4["ranges"]))
-    r0, rows = sharding.row_band(p4.H, rank, world)
-    assert all(sharding.row_band(p4.H, r, world)[1] == rows for r in range(world)), "bands must be equal for all_gather_into_tensor"
-    full = torch.zeros((p4.H, p4.W), dtype=torch.int8, device=dev)
+    full = torch.full((p4.H, p4.W), 5, dtype=torch.int8, device=dev)      # stale contents must all be overwritten
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    m.replay_dev(p4, 1, w4.n_frames, tx.data_ptr(), ty.data_ptr(), tyaw.data_ptr(), tr.data_ptr(), full.data_ptr(), row0=r0, rows=rows)
-    band = full[r0:r0 + rows].contiguous()
-    gathered = torch.empty((p4.H, p4.W), dtype=torch.int8, device=dev)
-    dist.all_gather_into_tensor(gathered, band)          # the single exchange of config 4
+    m.replay_banded_dev(p4, w4.n_frames, tx.data_ptr(), ty.data_ptr(), tyaw.data_ptr(), tr.data_ptr(), full.data_ptr(), gather=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    # the host-buffer form: each rank uploads 1/world of the log, NCCL all-gathers it
+    hgrid, st = m.replay_banded(p4, x[0], y[0], d4["frame_yaw_deg"][0], d4["ranges"][0], want_grid=(rank == 0))
+    want, U = o.replay(p4, x[0], y[0], d4["frame_yaw_deg"][0], d4["ranges"][0])
+    got = full.cpu().numpy()
+    assert np.array_equal(got, want), f"rank {rank}: {int((got != want).sum())} cells differ after the all-gather"
+    assert st["ray_cell_updates"] == U
     if rank == 0:
-        want, U = o.replay(p4, x[0], y[0], d4["frame_yaw_deg"][0], d4["ranges"][0])
-        got = gathered.cpu().numpy()
-        assert np.array_equal(got, want), f"{int((got != want).sum())} cells differ after the all-gather"
-        print(f"[multigpu] 16384^2 grid in {world} owned row bands + all-gather: byte-identical to the oracle "
-              f"({U} updates, {dt*1e3:.1f} ms incl. gather)", flush=True)
+        assert np.array_equal(hgrid, want), "host-buffer banded replay differs"
+        print(f"[multigpu] 16384^2 grid in {world} owned row bands + ncclAllGather inside libuqs_mapping (NCCL {m.nccl_version()}): "
+              f"byte-identical to the oracle on every rank ({U} updates, {dt*1e3:.1f} ms incl. gather)", flush=True)
         print("MULTIGPU_OK", flush=True)
+    m.comm_destroy()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -339,6 +339,52 @@ def test_pose_integration_nonfinite_yaw_follows_the_cpu_statement(gpu, oracle, s
 
 
 # ----------------------------------------------------------------------------------------------
+# other input / output forms of the host-buffer call: u16 millimetre ranges, boxed grids
+# ----------------------------------------------------------------------------------------------
+def test_millimetre_ranges_and_boxed_output(gpu, oracle, synth):
+    """uqs_replay_flow_mm (ranges as the sensor's u16 millimetres, converted on the device as uav_local_nav.c:1328
+    does) and uqs_replay_flow_boxed (touched boxes instead of dense grids) give the bytes of uqs_replay_flow."""
+    w = synth.on_mm_lattice(synth.scaled(synth.CONFIGS["c3"], n_flights=40, n_samples=700))
+    d = synth.generate(w)
+    p = w.params()
+    d["ranges"][3] = np.nan                                       # a flight without any return: an empty box
+    mm = synth.ranges_to_mm(d["ranges"])
+    assert np.array_equal(synth.mm_to_ranges(mm).view(np.uint32), d["ranges"].view(np.uint32))
+    args = (d["t_ms"], d["of_rate_x"], d["of_rate_y"], d["h_m"], d["yaw_deg"], d["of_q"])
+    g_f, px, py, st_f = gpu.replay_flow(p, *args, d["ranges"])
+    ox, oy = oracle.pose_integrate(*args)
+    want, U = oracle.replay_flights(p, ox, oy, d["frame_yaw_deg"], d["ranges"])
+    assert np.array_equal(g_f, want), first_diff(g_f, want)
+    g_mm, qx, qy, st_mm = gpu.replay_flow_mm(p, *args, mm)
+    assert np.array_equal(g_mm, want), first_diff(g_mm, want)
+    assert st_mm == st_f and st_f["ray_cell_updates"] == U
+    assert np.array_equal(qx.view(np.uint32), ox.view(np.uint32))
+    cells = 40 * p.W * p.H
+    for kw in ({"ranges_mm": mm}, {"ranges": d["ranges"]}):
+        for chunk in (0, 7):                                      # one chunk / six chunks through the pipeline
+            gpu.set_host_chunk(chunk)
+            try:
+                boxes, offs, packed, used, st_b = gpu.replay_flow_boxed(p, *args, **kw)
+            finally:
+                gpu.set_host_chunk(0)
+            dense = gpu.unpack_boxed(p, boxes, offs, packed)
+            assert np.array_equal(dense, want), first_diff(dense, want)
+            assert st_b["ray_cell_updates"] == U and used < 0.6 * cells
+            assert (boxes[3] == 0).all() and (boxes[0, 2] > boxes[0, 0]) and (boxes[:, 2] <= p.W).all()
+    # the sub-tile engine has no touched boxes: the box is the whole grid, the bytes are the same
+    gpu.set_engine(1, 0)
+    try:
+        boxes, offs, packed, used, _ = gpu.replay_flow_boxed(p, *args, ranges_mm=mm)
+    finally:
+        gpu.set_engine(0, 0)
+    assert np.array_equal(gpu.unpack_boxed(p, boxes, offs, packed), want)
+    # too small an output buffer is an error, never a truncated result
+    with pytest.raises(gpu.UqsError) as e:
+        gpu.replay_flow_boxed(p, *args, ranges_mm=mm, packed=np.empty(1000, np.int8))
+    assert e.value.code == gpu.ERR_NOMEM
+
+
+# ----------------------------------------------------------------------------------------------
 # inputs outside the fast engines' assumptions: the unrestricted kernel (uqs_generic.cu)
 # ----------------------------------------------------------------------------------------------
 def test_unrestricted_kernel_equals_oracle_on_ordinary_logs(gpu, oracle, synth):
