@@ -133,6 +133,10 @@ int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
  * such a grid), a clamp range that excludes 0, and accumulate != 0 onto a grid holding
  * values outside [lo_min, lo_max].  Nothing is refused or approximated. */
 int  uqs_set_engine(int engine, int flight_warps);
+/* Lane layout of the resident engine's free-space steps: 0 = the 32 beams of a frame x 1 step per warp
+ * instruction, 1 = the 8 beams of one sensor x 4 consecutive steps (fewer shared-memory bank conflicts).
+ * -1 = the built-in choice.  Identical bytes either way. */
+int  uqs_set_fan_layout(int on);
 
 /*
  * P0 -- dead-reckoning pose integration (BUILDER-DEFINED: the reference has no

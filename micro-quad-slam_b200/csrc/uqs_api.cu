@@ -325,7 +325,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         while (*ring > 32 && region + (size_t)(*ring + 4) * w + dec_bytes > kFlightSmemMax) *ring >>= 1;
         *bytes = region + (size_t)(*ring + 4) * w + dec_bytes;         // + one spare word per warp
         *ctas = 0;
-        return *bytes <= kFlightSmemMax ? flights_prepare(w, *bytes, ctas) : cudaSuccess;
+        return *bytes <= kFlightSmemMax ? flights_prepare(w, g_ctx.flight_fan, *bytes, ctas) : cudaSuccess;
       };
       if (g_ctx.flight_warps) {
         e = fit(fnw, &ring_size, &fsmem, &f_ctas);
@@ -370,7 +370,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         if (e != cudaSuccess) return cuda_fail(e, "memset before k_replay_flights");
         const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)f_ctas * g_ctx.sm_count);
         KernelTimer t_rep(2);
-        e = flights_launch(fnw, fgrid, fsmem, st, FA);
+        e = flights_launch(fnw, g_ctx.flight_fan, fgrid, fsmem, st, FA);
         t_rep.stop();
         if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights launch");
         g_ctx.launches += 2;
@@ -630,6 +630,13 @@ int uqs_set_engine(int engine, int flight_warps) {
   }
   g_ctx.engine = engine;
   g_ctx.flight_warps = flight_warps;
+  return UQS_OK;
+}
+
+/* Lane layout of the resident engine's free-space steps: 0 = 32 beams x 1 step, 1 = 8 beams of one sensor x 4
+ * consecutive steps (see k_replay_flights).  Identical bytes. */
+int uqs_set_fan_layout(int on) {
+  g_ctx.flight_fan = on < 0 ? kDefaultFanLayout : (on ? 1 : 0);
   return UQS_OK;
 }
 

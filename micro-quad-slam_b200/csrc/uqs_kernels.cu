@@ -16,6 +16,7 @@
 // can apply one ray's cells at once with plain byte read-modify-writes -- no
 // atomics, no races, bit-identical to the sequential loop.
 #include <algorithm>
+#include <cstdio>
 
 #include "uqs_kernels.cuh"
 
@@ -95,16 +96,23 @@ k_pose_chain(int n_flights, int n_samples, const float* __restrict__ inc_n,
     if (s0 + kChainChunk < n_samples) fetch(s0 + kChainChunk);     // in flight while lane 0 works through this chunk
     __syncwarp();
     if (lane == 0) {
-      const int cnt = min(kChainChunk, n_samples - s0);
-      for (int i = 0; i < cnt; i += 4) {                           // padding past the end holds zeros: harmless adds
-        float4 a = *reinterpret_cast<const float4*>(&sn[i]);
-        float4 b = *reinterpret_cast<const float4*>(&se[i]);
+      // the whole chunk is walked (padding past the end of the log holds zeros: harmless adds); the shared-memory loads
+      // run two groups of four ahead of the adds so that their latency (~29 cycles) never sits on the chain
+      const float4* vn = reinterpret_cast<const float4*>(sn);
+      const float4* ve = reinterpret_cast<const float4*>(se);
+      float4 a0 = vn[0], b0 = ve[0], a1 = vn[1], b1 = ve[1];
+#pragma unroll 4
+      for (int g = 0; g < kChainChunk / 4; g++) {
+        const int gn = min(g + 2, kChainChunk / 4 - 1);
+        const float4 a2 = vn[gn], b2 = ve[gn];
+        float4 a = a0, b = b0;
         a.x = px = __fadd_rn(px, a.x); b.x = py = __fadd_rn(py, b.x);
         a.y = px = __fadd_rn(px, a.y); b.y = py = __fadd_rn(py, b.y);
         a.z = px = __fadd_rn(px, a.z); b.z = py = __fadd_rn(py, b.z);
         a.w = px = __fadd_rn(px, a.w); b.w = py = __fadd_rn(py, b.w);
-        *reinterpret_cast<float4*>(&sn[i]) = a;
-        *reinterpret_cast<float4*>(&se[i]) = b;
+        reinterpret_cast<float4*>(sn)[g] = a;
+        reinterpret_cast<float4*>(se)[g] = b;
+        a0 = a1; b0 = b1; a1 = a2; b1 = b2;
       }
     }
     __syncwarp();
@@ -500,6 +508,23 @@ __device__ __forceinline__ bool box_overlaps(uint32_t xlohi, uint32_t ylohi, int
   return bx0 < X1 && bx1 >= X0 && by0 < Y1 && by1 >= Y0;
 }
 
+// -DUQS_DEBUG_BOUNDS (make debug -> libuqs_mapping_dbg.so): every shared-memory access of the replay kernels is
+// checked against the region it is meant for -- a flight's resident box, a warp's collision table, the decode ring,
+// a warp's sub-tile, its candidate queue -- and traps with a message otherwise.  compute-sanitizer is closed on the
+// pool this was developed on; a stray write into a neighbouring region need not show in the grids, so byte parity
+// alone would not catch it.  tests/test_gpu_debug_bounds.py runs the stress and ragged cases under this build.
+struct SmemRegion { uint32_t lo, hi; };
+#ifdef UQS_DEBUG_BOUNDS
+__device__ __noinline__ void uqs_bounds_fail(uint32_t a, uint32_t n, uint32_t lo, uint32_t hi, int line) {
+  printf("UQS_DEBUG_BOUNDS: shared access [%u, %u) outside region [%u, %u) at uqs_kernels.cu:%d (block %d thread %d)\n", a, a + n,
+         lo, hi, line, (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
+#define UQS_CHECK(a, n, R) do { const uint32_t a_ = (a); if (a_ < (R).lo || a_ + (n) > (R).hi) uqs_bounds_fail(a_, (n), (R).lo, (R).hi, __LINE__); } while (0)
+#else
+#define UQS_CHECK(a, n, R) ((void)0)
+#endif
+
 // shared-memory byte access through 32-bit shared addresses (no generic->shared conversion per use)
 __device__ __forceinline__ int lds_s8(uint32_t a) {
   int v;
@@ -533,6 +558,7 @@ __device__ __forceinline__ int in_reg(int v) {
 
 
 struct TileConsts { int pitch, lo_free, lo_occ, lo_min, lo_max, end_nohit; };
+struct TileRegions { SmemRegion tile, queue; };      // debug bounds of the current job (unused in release builds)
 
 // floor(num / den) for 0 <= num < 2^22, 1 <= den <= 1024: one reciprocal multiply and a +-1 fix-up
 // (num is exact in binary32; the product is within 1 of the quotient).
@@ -570,12 +596,14 @@ static_assert(kQueueBytes == kReplayQueueBytes, "the host sizes the queues");
 //   outside +-(lo_max-lo_min)) only matters while f(lo_min) < f(lo_max), and then it never saturated
 //   ("time slices").  k_compose_slices applies the maps in slice order.
 template <bool MAP>
-__device__ __forceinline__ void apply_queued(const TileConsts& A, uint32_t tile, int lane, uint32_t queue, int head,
+__device__ __forceinline__ void apply_queued(const TileConsts& A, const TileRegions& DR, uint32_t tile, int lane, uint32_t queue, int head,
                                              int count, int X0, int X1, int Y0, int Y1) {
+  (void)DR;
   uint32_t p1, p2, p3, p4, inv_l;      // n2 | m<<16 ; cK | cQ<<16 ; ka | kb<<11 | hit<<22 ; origin address ; reciprocal
   bool live;
   {
     const uint32_t at = queue + 4u * (uint32_t)((head + lane) & (kQueueEntries - 1));
+    UQS_CHECK(at, 4u, DR.queue); UQS_CHECK(at + 8u * kQueueEntries, 4u, DR.queue);
     const uint32_t w0 = lds_u32(at), org = lds_u32(at + 8u * kQueueEntries);
     inv_l = lds_u32(at + 4u * kQueueEntries);
     const int gx0 = (int)(org & 0xffffu), gy0 = (int)(org >> 16);
@@ -624,10 +652,12 @@ __device__ __forceinline__ void apply_queued(const TileConsts& A, uint32_t tile,
       const int delta = (k == m) ? end_delta : -A.lo_free;
       if (!MAP) {
         const uint32_t cell = base + (uint32_t)(k * cK + q * cQ);
+        UQS_CHECK(cell, 1u, DR.tile);
         const int v = lds_s8(cell) + delta;
         sts_u8(cell, min(max(v, A.lo_min), A.lo_max));
       } else {
         const uint32_t cell = base + ((uint32_t)(k * cK + q * cQ) << 2);
+        UQS_CHECK(cell, 4u, DR.tile);
         const uint32_t w = lds_u32(cell);
         int flo = (int)(int8_t)(w & 0xffu), fhi = (int)(int8_t)((w >> 8) & 0xffu), a = (int)w >> 16;
         flo = min(max(flo + delta, A.lo_min), A.lo_max);
@@ -678,6 +708,12 @@ k_replay_tiles(ReplayArgs A) {
     int8_t* grid = A.grids + (size_t)flight * A.W * A.H;
     const bool vec = ((A.W | X0 | tw) & 3) == 0 && ((reinterpret_cast<size_t>(grid) & 3) == 0);
     const bool map = slice > 0;
+    TileRegions DR;
+    DR.tile.lo = tile_s;
+    DR.tile.hi = tile_s + (uint32_t)(map ? A.pitch_cells * th * 4 : A.pitch * th);
+    DR.queue.lo = queue_s;
+    DR.queue.hi = queue_s + (uint32_t)kQueueBytes;
+    (void)DR;
 
     // ---- start state: the grid (accumulate), zeros, or the identity map -----------------
     if (map) {
@@ -713,8 +749,8 @@ k_replay_tiles(ReplayArgs A) {
     auto flush = [&]() {
       const int count = min(qn, 32);
       __syncwarp();
-      if (map) apply_queued<true>(CM, tile_s, lane, queue_s, qhead, count, X0, X1, Y0, Y1);
-      else     apply_queued<false>(CV, tile_s, lane, queue_s, qhead, count, X0, X1, Y0, Y1);
+      if (map) apply_queued<true>(CM, DR, tile_s, lane, queue_s, qhead, count, X0, X1, Y0, Y1);
+      else     apply_queued<false>(CV, DR, tile_s, lane, queue_s, qhead, count, X0, X1, Y0, Y1);
       qhead = (qhead + count) & (kQueueEntries - 1);
       qn -= count;
     };
@@ -749,6 +785,7 @@ k_replay_tiles(ReplayArgs A) {
           if (nm == 0u) continue;
           if (near) {
             const uint32_t at = queue_s + 4u * (uint32_t)((qhead + qn + __popc(nm & ((1u << lane) - 1u))) & (kQueueEntries - 1));
+            UQS_CHECK(at, 4u, DR.queue); UQS_CHECK(at + 8u * kQueueEntries, 4u, DR.queue);
             sts_u32(at, rec.x);
             sts_u32(at + 4u * kQueueEntries, rec.y);
             sts_u32(at + 8u * kQueueEntries, (uint32_t)gx0 | ((uint32_t)gy0 << 16));
@@ -857,7 +894,15 @@ __device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int bx0
 #ifndef UQS_MINB
 #define UQS_MINB 8
 #endif
-template <int NW>
+// FAN = 1: the free-space steps are laid out as 8 beams of ONE sensor x 4 consecutive steps per warp instruction
+// (warp w serves sensor w & 3; the NW/4 warps of a sensor interleave blocks of 4 steps) instead of 32 beams x 1 step.
+// The eight beams of a 63-degree fan sit in eight different rows (or columns) and the four steps of a beam in one or
+// two neighbouring words, so an access costs ~1.9 shared-memory wavefronts instead of ~2.4 (simulated on the
+// ensemble's geometry, tools/banksim.py; the four fans of a frame land in unrelated banks, which is what makes the
+// 32-beam layout conflict), and the lanes are fuller (25 of 32 instead of 22.7: a short fan no longer idles its lanes
+// through the long fans' steps).  Same cells, same order constraints: every (beam, step >= K0) cell of a frame is
+// touched by exactly one lane, whichever layout enumerates them.
+template <int NW, int FAN>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? UQS_MINB : ((NW <= 8) ? 4 : ((NW <= 16) ? 2 : 1)))
 k_replay_flights(FlightArgs A) {
   int8_t* grid_s = reinterpret_cast<int8_t*>(uqs_smem);
@@ -913,6 +958,11 @@ k_replay_flights(FlightArgs A) {
 
     const uint4* frames = A.frames + (size_t)flight * A.n_frames;
     const uint2* rays = A.rays + (size_t)flight * A.n_frames * 32;
+    // debug bounds: this flight's resident box, this warp's collision table, the decode ring
+    const SmemRegion RG = { grid_sa, grid_sa + (uint32_t)(P * bh) };
+    const SmemRegion RR = { ring_sa, ring_sa + (uint32_t)A.ring_size };
+    const SmemRegion RD = { dec_sa, dec_sa + (uint32_t)((NW < kDecSlotsMax ? NW : kDecSlotsMax) * kDecSlotBytes) };
+    (void)RG; (void)RR; (void)RD;
     // Beam decode is shared: warp (f mod NW) decodes frame f + L into a ring of R = min(NW, 4) slots in shared memory
     // (32 lanes x 2 x 16 B + one frame record per slot); every warp then reads its lane's 32 B per frame.  A warp
     // therefore decodes -- and loads raw records for -- only every NW-th frame, one turn ahead.
@@ -923,6 +973,7 @@ k_replay_flights(FlightArgs A) {
       const int mx = __reduce_max_sync(0xffffffffu, b.m);
       const uint32_t at = dec_sa + (uint32_t)slot * kDecSlotBytes;
       // 16 bytes per beam stored as the registers the free-space loop uses (no unpacking by the NW readers)
+      UQS_CHECK(at + 16u * (uint32_t)lane, 16u, RD); UQS_CHECK(at + 512u + 4u * (uint32_t)lane, 4u, RD); UQS_CHECK(at + 1024u, 16u, RD);
       sts_v4(at + 16u * (uint32_t)lane, b.inv, (uint32_t)b.n2, (uint32_t)b.m, (uint32_t)b.sM);
       // (the minor stride and what only the collision and end steps need share one word: sN | rb<0 | ra | end_delta)
       sts_u32(at + 512u + 4u * (uint32_t)lane, ((uint32_t)b.sN << 16) | (b.rb < 0 ? 0x1000u : 0u) | ((uint32_t)b.ra << 8) |
@@ -941,9 +992,15 @@ k_replay_flights(FlightArgs A) {
     __syncthreads();
     for (int f = 0; f < A.n_frames; f++) {
       const uint32_t at = dec_sa + (uint32_t)(f & (R - 1)) * kDecSlotBytes;
-      const uint4 dv = lds_v4(at + 16u * (uint32_t)lane);
-      const uint32_t dw = lds_u32(at + 512u + 4u * (uint32_t)lane);
+      UQS_CHECK(at + 16u * (uint32_t)lane, 16u, RD); UQS_CHECK(at + 1024u, 16u, RD);
       const uint4 fv = lds_v4(at + 1024u);
+      // lane = beam parameters: everything without FAN; with FAN only the warps that have a collision step this frame
+      uint4 dv = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t dw = 0u;
+      if (!FAN || ((w - f - 1) & (NW - 1)) < (int)fv.y) {
+        dv = lds_v4(at + 16u * (uint32_t)lane);
+        dw = lds_u32(at + 512u + 4u * (uint32_t)lane);
+      }
       const uint32_t inv = dv.x;
       const int n2 = (int)dv.y, m = (int)dv.z, h2 = m & ~1;
       const int sM = (int)dv.w, sN = (int)dw >> 16;
@@ -987,6 +1044,7 @@ k_replay_flights(FlightArgs A) {
             }
             if (apply) {
               const uint32_t cell = grid_sa + (uint32_t)addr;
+              UQS_CHECK(cell, 1u, RG);
               sts_u8(cell, max(lds_s8(cell) - len * lo_free, lo_min));
             }
             __syncwarp();
@@ -1010,6 +1068,7 @@ k_replay_flights(FlightArgs A) {
           }
           if (apply) {
             const uint32_t cell = grid_sa + (uint32_t)addr;
+            UQS_CHECK(cell, 1u, RG);
             sts_u8(cell, max(lds_s8(cell) - len * lo_free, lo_min));
           }
           __syncwarp();
@@ -1024,13 +1083,14 @@ k_replay_flights(FlightArgs A) {
         int pos = B.ra * k + B.rb * q;
         if (pos == 8 * k) pos = 0;
         const int slot = pos & ring_mask;
-        if (head) sts_u8(ring_sa + (uint32_t)slot, lane);
+        if (head) { UQS_CHECK(ring_sa + (uint32_t)slot, 1u, RR); sts_u8(ring_sa + (uint32_t)slot, lane); }
         __syncwarp();
         const bool lost = head && lds_s8(ring_sa + (uint32_t)slot) != lane;
         const unsigned boundm = __ballot_sync(0xffffffffu, bound);
         const unsigned actm = __ballot_sync(0xffffffffu, act);
         unsigned pend = __ballot_sync(0xffffffffu, lost);
         const uint32_t cell = grid_sa + (uint32_t)addr;
+        if (act) UQS_CHECK(cell, 1u, RG);
         if ((boundm & actm) == actm && pend == 0u) {
           if (act) sts_u8(cell, min(max(lds_s8(cell) + delta, lo_min), lo_max));
         } else {
@@ -1063,12 +1123,49 @@ k_replay_flights(FlightArgs A) {
         __syncwarp();      // ring[] is rewritten by the next step
       }
 
-      // ---- steps k >= K0: every cell is touched by one beam only; UN steps in flight, no branches
-      // (lanes past their beam's end are predicated off)
-      int k = B.k0 + ((w - B.k0) & (NW - 1));          // first step >= K0 of this warp's residue class
       const uint32_t gbase = grid_sa + (uint32_t)base;
       const int free_delta = -lo_free;
       constexpr int UN = UQS_UN;                    // steps in flight per warp
+      if (FAN) {
+        // ---- steps k >= K0, fan layout: lane = (beam of this warp's sensor, one of 4 consecutive steps) -----------
+        constexpr int NS = NW / 4;                  // warps per sensor
+        const uint32_t bq = (uint32_t)((w & 3) * 8 + (lane >> 2));
+        const int j = lane & 3;
+        UQS_CHECK(at + 16u * bq, 16u, RD); UQS_CHECK(at + 512u + 4u * bq, 4u, RD);
+        const uint4 ev = lds_v4(at + 16u * bq);
+        const uint32_t ew = lds_u32(at + 512u + 4u * bq);
+        const uint32_t inv_f = ev.x;
+        const int n2_f = (int)ev.y, m_f = (int)ev.z, h2_f = m_f & ~1, sM_f = (int)ev.w, sN_f = (int)ew >> 16;
+        const int fmax = __reduce_max_sync(0xffffffffu, m_f);          // longest beam of the fan
+        int kb = kshared + 4 * (w >> 2);                                // first block of 4 steps of this warp
+        int mu[UN];                                                     // kb + j + u*4*NS < m_f  <=>  kb < mu[u]
+#pragma unroll
+        for (int u = 0; u < UN; u++) mu[u] = in_reg(m_f - j - u * 4 * NS);
+        for (; kb < fmax; kb += UN * 4 * NS) {
+          uint32_t addr[UN];
+          int val[UN];
+          bool on[UN];
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            const int ku = kb + j + u * 4 * NS;
+            addr[u] = gbase + (uint32_t)(ku * sM_f + minor_steps(ku, n2_f, h2_f, inv_f) * sN_f);
+            on[u] = kb < mu[u];
+          }
+#pragma unroll
+          for (int u = 0; u < UN; u++) if (on[u]) { UQS_CHECK(addr[u], 1u, RG); val[u] = lds_s8(addr[u]); }
+#pragma unroll
+          for (int u = 0; u < UN; u++) if (on[u]) sts_u8(addr[u], __viaddmax_s32(val[u], free_delta, lo_min));
+        }
+        // end cells of the fan's beams that end at a step >= K0: one lane per beam, one warp per sensor
+        if ((w >> 2) == ((f + 1) & (NS - 1)) && j == 0 && m_f >= kshared) {
+          const uint32_t cell = gbase + (uint32_t)(m_f * sM_f + (n2_f >> 1) * sN_f);
+          UQS_CHECK(cell, 1u, RG);
+          sts_u8(cell, min(max(lds_s8(cell) + (int)(signed char)(ew & 0xffu), lo_min), lo_max));
+        }
+      } else {
+      // ---- steps k >= K0: every cell is touched by one beam only; UN steps in flight, no branches
+      // (lanes past their beam's end are predicated off)
+      int k = B.k0 + ((w - B.k0) & (NW - 1));          // first step >= K0 of this warp's residue class
       // free-space steps K0 <= k < m only: clamp(v - free) = max(v - free, lo_min) because lo_free >= 0 (one
       // VIADDMNMX); the end cells of these beams are one extra step of one warp below
       int mu[UN];                                   // k + u*NW < m  <=>  k < mu[u]
@@ -1085,7 +1182,7 @@ k_replay_flights(FlightArgs A) {
           on[u] = k < mu[u];
         }
 #pragma unroll
-        for (int u = 0; u < UN; u++) if (on[u]) val[u] = lds_s8(addr[u]);
+        for (int u = 0; u < UN; u++) if (on[u]) { UQS_CHECK(addr[u], 1u, RG); val[u] = lds_s8(addr[u]); }
 #pragma unroll
         for (int u = 0; u < UN; u++) if (on[u]) sts_u8(addr[u], __viaddmax_s32(val[u], free_delta, lo_min));
         // (skipping the store for cells already at lo_min was measured 8 % slower: two more ISETPs per step)
@@ -1095,9 +1192,11 @@ k_replay_flights(FlightArgs A) {
       if (w == ((f + 1) & (NW - 1)) && mmax >= kshared) {
         if (m >= kshared) {
           const uint32_t cell = gbase + (uint32_t)(m * sM + (n2 >> 1) * sN);
+          UQS_CHECK(cell, 1u, RG);
           sts_u8(cell, min(max(lds_s8(cell) + B.end_delta, lo_min), lo_max));
         }
       }
+      }   // !FAN
       if ((f & (NW - 1)) == w) {                    // this warp's turn: decode frame f + L, prefetch its next turn
         const int g = f + L;
         if (g < A.n_frames) decode_store(raw_rec, raw_org, g & (R - 1));
@@ -1152,8 +1251,9 @@ __global__ void k_flight_boxes(int n_flights, int groups_per_flight, const uint2
   }
 }
 
-static void (*flight_kernel(int nw))(FlightArgs) {
-  return nw == 4 ? k_replay_flights<4> : (nw == 8 ? k_replay_flights<8> : (nw == 32 ? k_replay_flights<32> : k_replay_flights<16>));
+static void (*flight_kernel(int nw, int fan))(FlightArgs) {
+  if (fan) return nw == 4 ? k_replay_flights<4, 1> : (nw == 8 ? k_replay_flights<8, 1> : (nw == 32 ? k_replay_flights<32, 1> : k_replay_flights<16, 1>));
+  return nw == 4 ? k_replay_flights<4, 0> : (nw == 8 ? k_replay_flights<8, 0> : (nw == 32 ? k_replay_flights<32, 0> : k_replay_flights<16, 0>));
 }
 
 // dims -> mapped host memory: a device-to-host memcpy of these two words would queue on the D2H copy engine
@@ -1171,14 +1271,14 @@ cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint
   return cudaGetLastError();
 }
 
-cudaError_t flights_prepare(int nw, size_t smem, int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(flight_kernel(nw), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t flights_prepare(int nw, int fan, size_t smem, int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(flight_kernel(nw, fan), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, flight_kernel(nw), nw * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, flight_kernel(nw, fan), nw * 32, smem);
 }
 
-cudaError_t flights_launch(int nw, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A) {
-  flight_kernel(nw)<<<grid, nw * 32, smem, st>>>(A);
+cudaError_t flights_launch(int nw, int fan, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A) {
+  flight_kernel(nw, fan)<<<grid, nw * 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 

@@ -26,6 +26,9 @@ def build(force: bool = False):
     if force or not os.path.exists(ORC_LIB) or os.path.getmtime(ORC_LIB) < os.path.getmtime(os.path.join(HERE, "uqs_oracle.c")):
         subprocess.check_call(["make", "-C", HERE, "liborc.so"], stdout=subprocess.DEVNULL)
     subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+    # the real reference translation unit against the product library (needs the library: skipped until it is built)
+    if os.path.exists(os.path.join(os.path.dirname(HERE), "micro-quad-slam_b200", "libuqs_mapping.so")):
+        subprocess.check_call(["bash", os.path.join(HERE, "link_reference.sh")], stdout=subprocess.DEVNULL)
 
 
 def _vp(a: Optional[np.ndarray]):

@@ -11,13 +11,18 @@ from conftest import first_diff, have_ref
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tiles", "resident4", "resident8", "resident16", "resident32"])
+@pytest.fixture(params=["tiles", "resident4", "resident8", "resident16", "resident32", "resident4fan", "resident8fan", "resident16fan",
+                        "resident32fan"])
 def engine(request, gpu):
-    """Both replay engines (and the resident engine's warp counts) must give identical bytes."""
-    e, nw = {"tiles": (1, 0), "resident4": (2, 4), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[request.param]
+    """Both replay engines (the resident engine's warp counts and both of its lane layouts) must give identical bytes."""
+    name = request.param
+    fan = name.endswith("fan")
+    e, nw = {"tiles": (1, 0), "resident4": (2, 4), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[name[:-3] if fan else name]
     gpu.set_engine(e, nw)
-    yield request.param
+    gpu.set_fan_layout(1 if fan else 0)
+    yield name
     gpu.set_engine(0, 0)
+    gpu.set_fan_layout(-1)
 
 
 def oracle_grids(oracle, p, d, x=None, y=None):
@@ -797,16 +802,18 @@ def test_random_geometry_and_sensor_constants(gpu, oracle, seed):
     r[rng.random(r.shape) < 0.1] = np.nan
     r[rng.random(r.shape) < 0.1] = np.float32(rng.uniform(0.04, 3 * res))       # very short rays
     want, U = oracle.replay_flights(p, x, y, yaw, r)
-    cases = [(1, 0, 1), (1, 0, 3), (0, 0, 0)]
+    cases = [(1, 0, 1, 0), (1, 0, 3, 0), (0, 0, 0, 0)]
     if max(W, H) <= 400:
-        cases += [(2, 4, 0), (2, 16, 0)]
+        cases += [(2, 4, 0, 0), (2, 16, 0, 0), (2, 4, 0, 1), (2, 8, 0, 1), (2, 32, 0, 1)]
     try:
-        for engine, nw, slices in cases:
+        for engine, nw, slices, fan in cases:
             gpu.set_engine(engine, nw)
+            gpu.set_fan_layout(fan)
             gpu.set_tuning(0, 0, slices)
             got, st = gpu.replay(p, x, y, yaw, r)
-            assert np.array_equal(got, want), ((engine, nw, slices), dict(W=W, H=H, res=res, fov=float(p.fov_deg)), first_diff(got, want))
+            assert np.array_equal(got, want), ((engine, nw, slices, fan), dict(W=W, H=H, res=res, fov=float(p.fov_deg)), first_diff(got, want))
             assert st["ray_cell_updates"] == U
     finally:
         gpu.set_engine(0, 0)
+        gpu.set_fan_layout(-1)
         gpu.set_tuning(0, 0, 0)
