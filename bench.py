@@ -809,6 +809,7 @@ def main():
         replay_ms = ex["kms"][2] / max(ex["steps"], 1)
         achieved = b_alg / (replay_ms * 1e-3) / 1e9 if replay_ms > 0 else 0.0
         rmw_peak = m.measure_rmw_peak()
+        atoms_peak = m.measure_atoms_peak()
         cap = recorded_capture(w3, ex.get("F")) if args.workload == "c3" else {}
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src, "traffic": cap.get("dram_bytes_per_launch"),
@@ -821,7 +822,9 @@ def main():
                                                    "the pipe this kernel is bound by"},
                     "onchip_rmw": {"achieved_updates_per_s": U_r / (replay_ms * 1e-3) if replay_ms > 0 else 0.0, "peak_updates_per_s": rmw_peak,
                                    "frac": (U_r / (replay_ms * 1e-3) / rmw_peak) if replay_ms > 0 else 0.0,
-                                   "note": "peak = conflict-free shared-memory byte RMW microbenchmark on this GPU"}}
+                                   "atomics_updates_per_s": atoms_peak,
+                                   "note": "peak = conflict-free shared-memory byte load/clamp/store microbenchmark on this GPU; "
+                                           "atomics_updates_per_s = the same pattern with one ATOMS.ADD per update (the rejected design)"}}
 
         if not args.no_cpu_baseline and world == 1 and args.workload == "c3":
             d = ex["d_pinned"]

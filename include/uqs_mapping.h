@@ -340,6 +340,9 @@ int uqs_set_copy_only(int on);
 /* Measured on-chip read-modify-write ceiling: every warp of a full grid does
  * conflict-free byte RMWs on its shared-memory sub-tile.  Returns updates/s. */
 int uqs_measure_rmw_peak(double* updates_per_s);
+/* The same pattern with one shared-memory ATOMIC per update (ATOMS.ADD on 32-bit words): what the "integer
+ * log-odds atomics" of the original sketch would cost per update, clamp not included.  Returns updates/s. */
+int uqs_measure_atoms_peak(double* updates_per_s);
 
 /* ------------------------------------------------------------------------ */
 /* (1) Drop-in symbols (replace uav_local_nav.c:188-192, 205-216, 229, 241-306) */

@@ -83,7 +83,7 @@ _EXPORTS = [
     "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_set_fan_layout", "uqs_kernel_launches",
     "uqs_set_profiling", "uqs_profile_collect", "uqs_profile_timeline", "uqs_set_host_chunk",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
-    "uqs_beam_cells", "uqs_frame_bounds", "uqs_sincosf_batch", "uqs_measure_rmw_peak",
+    "uqs_beam_cells", "uqs_frame_bounds", "uqs_sincosf_batch", "uqs_measure_rmw_peak", "uqs_measure_atoms_peak",
     "uqs_beams_from_scans", "uqs_beams_from_scans_dev", "uqs_replay_recentering", "uqs_frontier_scores",
     "uqs_scanlog_read", "uqs_scanlog_count", "uqs_navlog_read", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
     # multi-GPU
@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
     L.uqs_frame_bounds.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp]
     L.uqs_sincosf_batch.argtypes = [C.c_size_t, vp, vp, vp]
     L.uqs_measure_rmw_peak.argtypes = [C.POINTER(C.c_double)]
+    L.uqs_measure_atoms_peak.argtypes = [C.POINTER(C.c_double)]
     L.uqs_beams_from_scans.argtypes = [C.c_longlong, vp, C.c_float, vp, vp]
     L.uqs_replay_recentering.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp, ip, C.POINTER(Stats)]
     L.uqs_frontier_scores.argtypes = [C.POINTER(Params), vp, ip, vp, vp, vp, vp, vp]
@@ -574,6 +575,13 @@ def grid_hash(grid: np.ndarray) -> int:
 
 def set_copy_only(on: bool):
     _check(lib().uqs_set_copy_only(1 if on else 0))
+
+
+def measure_atoms_peak() -> float:
+    """Shared-memory atomic (ATOMS.ADD) update rate, conflict-free: the price of the north star's atomics sketch."""
+    v = C.c_double(0)
+    _check(lib().uqs_measure_atoms_peak(C.byref(v)))
+    return float(v.value)
 
 
 def measure_rmw_peak() -> float:

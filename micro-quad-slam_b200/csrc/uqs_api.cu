@@ -881,4 +881,38 @@ int uqs_measure_rmw_peak(double* updates_per_s) {
   return UQS_OK;
 }
 
+/* Shared-memory ATOMIC update rate (ATOMS.ADD, conflict-free addresses, eight in flight per warp): the price of the
+ * north star's "integer log-odds atomics", reported by bench.py next to uqs_measure_rmw_peak(). */
+int uqs_measure_atoms_peak(double* updates_per_s) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (!updates_per_s) { set_error("NULL output"); return UQS_ERR_BAD_ARG; }
+  cudaStream_t st = g_ctx.stream();
+  const int tile_bytes = 4096, iters = 2048;
+  const size_t smem = (size_t)tile_bytes * kReplayWarps;
+  cudaError_t e = cudaFuncSetAttribute(k_atoms_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_atoms_peak)");
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_atoms_peak, kReplayThreads, smem);
+  if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "occupancy(k_atoms_peak)");
+  if ((rc = g_ctx.w->counters.ensure(64 * 8))) return rc;
+  const unsigned grid = (unsigned)(per_sm * g_ctx.sm_count);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  k_atoms_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, 64, (int*)g_ctx.w->counters.p + 96);
+  cudaEventRecord(a, st);
+  k_atoms_peak<<<grid, kReplayThreads, smem, st>>>(tile_bytes, iters, (int*)g_ctx.w->counters.p + 96);
+  cudaEventRecord(b, st);
+  e = cudaEventSynchronize(b);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (e != cudaSuccess) return cuda_fail(e, "k_atoms_peak");
+  *updates_per_s = (double)grid * kReplayThreads * (double)iters * 8.0 / (ms * 1e-3);
+  g_ctx.launches += 2;
+  return UQS_OK;
+}
+
 }  // extern "C"

@@ -1332,4 +1332,26 @@ k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink) {
   if (tile[lane] == 77) *sink = 1;
 }
 
+// The north star's sketch ("shared-memory grid tiles with integer log-odds atomics") measured: the same conflict-free
+// access pattern as k_rmw_peak, but each update is one shared-memory atomic (ATOMS.ADD on a 32-bit word -- the
+// hardware has no byte-wide shared atomic, so an int8 grid would need 4x the shared memory or a CAS loop on top of
+// this).  bench.py reports the rate next to the plain load/clamp/store rate; it cannot express the per-update clamp
+// anyway (uav_local_nav.c:259-260), this only prices the instruction.
+__global__ void __launch_bounds__(kReplayThreads)
+k_atoms_peak(int tile_bytes, int iters, int* sink) {
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  int* tile = reinterpret_cast<int*>(uqs_smem + (size_t)wic * tile_bytes);
+  for (int i = lane; i < tile_bytes / 4; i += 32) tile[i] = 0;
+  __syncwarp();
+  const uint32_t mask = (uint32_t)(tile_bytes / 4) - 1u;
+  uint32_t off = (uint32_t)lane;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) atomicAdd(&tile[(off + 32u * u) & mask], -1);
+    off += 256u + 32u;
+  }
+  __syncwarp();
+  if (tile[lane] == 77) *sink = 1;
+}
+
 }  // namespace uqs

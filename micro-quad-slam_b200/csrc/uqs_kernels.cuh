@@ -80,6 +80,7 @@ cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint
 cudaError_t flights_prepare(int nw, int fan, size_t smem, int* ctas_per_sm);
 cudaError_t flights_launch(int nw, int fan, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);
+__global__ void k_atoms_peak(int tile_bytes, int iters, int* sink);
 // uqs_next.cu
 __global__ void k_recenter_decide_one(float res, float size_m, float ox, float oy, float x, float y, int* out);
 __global__ void k_recenter_shift(const int8_t* src, int8_t* dst, int W, int H, int sx, int sy);

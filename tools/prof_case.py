@@ -8,6 +8,7 @@ dev = torch.device("cuda:0")
 m.set_stream(torch.cuda.current_stream().cuda_stream)
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 m.set_engine(int(sys.argv[2]) if len(sys.argv) > 2 else 0, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+m.set_fan_layout(int(sys.argv[4]) if len(sys.argv) > 4 else -1)
 w = syn.scaled(syn.CONFIGS["c3"], n_flights=nf)
 d = syn.generate(w); p = w.params()
 tx, ty, tyaw, tr = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (d["x_true"], d["y_true"], d["frame_yaw_deg"], d["ranges"]))
