@@ -602,13 +602,14 @@ def run_c4(cx, verify_n1):
     launches = m.kernel_launches() - l0
     kms, _ = m.profile_collect()
     m.set_profiling(False)
-    r0, rows = m.row_band(p.H, cx.rank, cx.world)
+    edges = m.band_edges()
     hh = int(m.grid_hashes_dev(grid.data_ptr(), 1, p.W * p.H)[0])
     rec = {"workload": f"BASELINE config 4: {w.name}", "samples": w.n_samples, "frames": NF, "beams_per_sample": 64,
            "grid": f"{p.W}x{p.H}", "value": U / (ms * 1e-3), "unit": "updates/s", "ms_per_step": ms, "updates": U,
            "frames_per_s": NF / (ms * 1e-3), "steps": steps, "warmup": warmup,
            "kernel_ms_rank0": {"ray_setup": kms[1] / steps, "replay": kms[2] / steps},
-           "partition": f"{cx.world} owned row bands of {rows} rows (uqs_row_band)", "exchange": "one ncclAllGather of the bands inside libuqs_mapping, in the timed region",
+           "partition": f"{cx.world} owned row bands cut at rows {edges} (equal shares of the log: origin-row histogram widened by the "
+                        "sensor's reach, computed on the device every call)", "exchange": "one ncclAllGather of the bands inside libuqs_mapping, in the timed region",
            "comm_nranks_seen": [m.comm_nranks()], "nccl_version": m.nccl_version() if cx.world > 1 else None,
            "what": "ray set-up + band replay + band all-gather, log resident in HBM on every rank",
            "hash": f"{hh:016x}", "hash_identical_on_every_rank": cx.all_equal(hh), "gpu_launches": int(launches)}

@@ -50,11 +50,9 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%s\n", uqs_last_error());
     return 1;
   }
-  for (int r = 0; r < n_gpus; r++) {
-    int r0, rows;
-    uqs_row_band(p.H, r, n_gpus, 4, &r0, &rows);
-    printf("gpu %d owns rows [%d, %d)\n", r, r0, r0 + rows);
-  }
+  int edges[17];
+  const int nb = uqs_band_edges(edges);                 /* cuts that give every GPU the same share of the log */
+  for (int r = 0; r < nb; r++) printf("gpu %d owns rows [%d, %d)\n", r, edges[r], edges[r + 1]);
   /* the same log on one GPU */
   if (uqs_multi_select(0) || uqs_replay(&p, 1, (int)n, x, y, yaw, beams, grid_one, &st1)) {
     fprintf(stderr, "%s\n", uqs_last_error());

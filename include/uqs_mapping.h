@@ -300,6 +300,15 @@ int uqs_comm_destroy(void);
 int uqs_comm_nranks(void);
 int uqs_comm_rank(void);
 int uqs_nccl_version(void);            /* e.g. 22809; 0 if NCCL cannot be loaded */
+/* Where the banded replays cut the grid: 1 (default) = so that every rank gets the same share of the LOG -- a
+ * histogram of the frames' origin rows widened by the sensor's reach, computed on the device from the log each
+ * call (a sweep that covers the middle of a large grid would leave equal outer bands idle); 0 = equal bands
+ * (uqs_row_band).  Every rank derives the same cuts from the same log; any cuts give identical bytes.
+ * uqs_band_edges: edges_out[0..nranks] of the last banded replay, returns nranks. */
+int uqs_set_band_balance(int on);
+int uqs_balanced_row_bands_dev(const uqs_params* p, int n_frames, const float* x_dev, const float* y_dev,
+                               int world, int* edges_out /* [world + 1] */);
+int uqs_band_edges(int* edges_out);
 /* Config 4 on this rank: replay this rank's owned row band of ONE W x H grid from a log that every rank holds
  * on its device, then (gather != 0) the path's single exchange: the disjoint bands are all-gathered over NCCL so
  * that every rank holds the whole grid.  grid_dev addresses the full W*H grid.  Asynchronous on the current

@@ -88,7 +88,7 @@ _EXPORTS = [
     "uqs_scanlog_read", "uqs_scanlog_count", "uqs_navlog_read", "map_recenter_shift", "map_recentre_if_needed", "frontier_score_dir",
     # multi-GPU
     "uqs_flight_shard", "uqs_row_band", "uqs_comm_unique_id", "uqs_comm_init_rank", "uqs_comm_destroy", "uqs_comm_nranks",
-    "uqs_comm_rank", "uqs_nccl_version", "uqs_replay_banded_dev", "uqs_replay_banded", "uqs_multi_init", "uqs_multi_count",
+    "uqs_comm_rank", "uqs_nccl_version", "uqs_set_band_balance", "uqs_band_edges", "uqs_balanced_row_bands_dev", "uqs_replay_banded_dev", "uqs_replay_banded", "uqs_multi_init", "uqs_multi_count",
     "uqs_multi_select", "uqs_multi_shutdown", "uqs_multi_replay_banded", "uqs_multi_grid_dev",
     "uqs_grid_hashes_dev", "uqs_grid_hash", "uqs_set_copy_only", "uqs_replay_flow_mm", "uqs_replay_flow_boxed", "uqs_unpack_boxed",
     # drop-in symbols
@@ -145,6 +145,9 @@ def lib() -> C.CDLL:
     L.uqs_flight_shard.restype = None
     L.uqs_row_band.argtypes = [ip, ip, ip, ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.uqs_row_band.restype = None
+    L.uqs_set_band_balance.argtypes = [ip]
+    L.uqs_band_edges.argtypes = [C.POINTER(C.c_int)]
+    L.uqs_balanced_row_bands_dev.argtypes = [C.POINTER(Params), ip, vp, vp, ip, C.POINTER(C.c_int)]
     L.uqs_comm_unique_id.argtypes = [vp]
     L.uqs_comm_init_rank.argtypes = [vp, ip, ip]
     L.uqs_replay_banded_dev.argtypes = [C.POINTER(Params), ip, vp, vp, vp, vp, vp, ip, C.POINTER(Stats)]
@@ -508,6 +511,24 @@ def comm_destroy():
 
 def comm_nranks() -> int:
     return int(lib().uqs_comm_nranks())
+
+
+def set_band_balance(on: bool = True):
+    _check(lib().uqs_set_band_balance(1 if on else 0))
+
+
+def balanced_row_bands_dev(p: Params, n_frames: int, x_ptr: int, y_ptr: int, world: int):
+    """``uqs_balanced_row_bands_dev``: the row cuts a ``world``-rank banded replay of this log would use."""
+    e = (C.c_int * (world + 1))()
+    _check(lib().uqs_balanced_row_bands_dev(C.byref(p), int(n_frames), C.c_void_p(x_ptr), C.c_void_p(y_ptr), int(world), e))
+    return list(e)
+
+
+def band_edges():
+    """Row cuts of the last banded replay: rank r owned rows [e[r], e[r+1])."""
+    e = (C.c_int * 17)()
+    n = lib().uqs_band_edges(e)
+    return list(e[:n + 1])
 
 
 def nccl_version() -> int:

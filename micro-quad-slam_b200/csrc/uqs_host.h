@@ -63,6 +63,7 @@ struct Context {
   void* pipeline = nullptr;                     // streams and staging of the host-buffer pipeline (uqs_pipeline.cu)
   void* comm = nullptr;                         // ncclComm_t of this device (uqs_multi.cu), nullptr = none
   int comm_rank = 0, comm_nranks = 1;
+  int band_edges[17] = { 0 };                   // row cuts of the last banded replay (uqs_band_edges)
 
   // optional per-kernel timing (uqs_set_profiling): event pairs on the launching stream
   bool profiling = false;

@@ -20,6 +20,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -87,6 +88,68 @@ BandBufs g_bands[kMaxDevices];
 
 }  // namespace
 
+// ---- balanced ownership --------------------------------------------------------------------------------------------
+// Equal row bands are only balanced when the flight covers the grid evenly; a building sweep covers the middle of a
+// 16384-row grid and leaves the outer bands idle.  The owned bands are therefore cut so that every rank gets the
+// same share of the log: a histogram of the frames' origin rows (device), widened by the sensor's reach (a frame
+// works on every band its rays can touch), and a prefix sum on the host.  Any partition gives the same bytes --
+// ownership is what makes the result exact, not where the cuts are -- and every rank derives the same cuts from
+// the same log.
+__global__ void k_row_histogram(const __grid_constant__ DevParams p, int n_frames, const float* __restrict__ x,
+                                const float* __restrict__ y, int align, unsigned* __restrict__ hist) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  int gx, gy;
+  if (world_to_grid(p, x[f], y[f], gx, gy)) atomicAdd(&hist[gy / align], 1u);
+}
+
+static int g_balance = 1;                          // uqs_set_band_balance
+
+// edges[0..world]: rank r owns rows [edges[r], edges[r+1]); multiples of `align` (except the last = H)
+static int band_edges(const DevParams& dp, int n_frames, const float* x_dev, const float* y_dev, int world, int align, int* edges) {
+  for (int r = 0; r <= world; r++) {
+    int r0, rows;
+    uqs_row_band(dp.H, std::min(r, world - 1), world, align, &r0, &rows);
+    edges[r] = r < world ? r0 : dp.H;
+  }
+  if (!g_balance || world <= 1) return UQS_OK;
+  const int units = (dp.H + align - 1) / align;
+  int rc = g_ctx.in_kind.ensure((size_t)units * sizeof(unsigned));
+  if (rc) return rc;
+  cudaStream_t st = g_ctx.stream();
+  unsigned* d_hist = (unsigned*)g_ctx.in_kind.p;
+  std::vector<unsigned> h(units);
+  cudaError_t e = zero_async(d_hist, (size_t)units * sizeof(unsigned), st);
+  if (e == cudaSuccess) {
+    k_row_histogram<<<(unsigned)((n_frames + 255) / 256), 256, 0, st>>>(dp, n_frames, x_dev, y_dev, align, d_hist);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_hist, (size_t)units * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "row histogram");
+  g_ctx.launches += 2;
+  // a frame at row y works on rows y +- reach: box filter of that width through prefix sums
+  const int reach = std::max(1, (int)std::ceil(dp.max_range / dp.res / (float)align) + 1);
+  std::vector<unsigned long long> pre(units + 1, 0), work(units + 1, 0);
+  for (int u = 0; u < units; u++) pre[u + 1] = pre[u] + h[u];
+  if (pre[units] == 0) return UQS_OK;                               // no frame on the grid: equal bands
+  for (int u = 0; u < units; u++) {
+    const int a = std::max(0, u - reach), b = std::min(units, u + reach + 1);
+    work[u + 1] = work[u] + (pre[b] - pre[a]);
+  }
+  const unsigned long long total = work[units];
+  int u = 0;
+  for (int r = 1; r < world; r++) {
+    const unsigned long long want = total / world * r + total % world * r / world;
+    while (u < units && work[u] < want) u++;
+    // every rank keeps at least one unit of rows (its ray set-up counts the log like everyone else's)
+    const int lo = edges[r - 1] + align, hi = dp.H - (world - r) * align;
+    edges[r] = hi >= lo ? std::min(std::max(u * align, lo), hi) : std::min(lo, dp.H);
+  }
+  edges[world] = dp.H;
+  return UQS_OK;
+}
+
 void comm_release() {
   if (g_ctx.comm && N.CommDestroy) N.CommDestroy((ncclComm_t)g_ctx.comm);
   g_ctx.comm = nullptr;
@@ -96,26 +159,25 @@ void comm_release() {
 
 // Gather the owned row bands of `grid` (full W*H on every rank, band r valid on rank r) so that every rank holds
 // the whole grid.  In place; equal bands: one ncclAllGather, ragged: one grouped ncclBroadcast per band.
-static int gather_bands(Context& c, int8_t* grid, int W, int H, cudaStream_t st) {
+static int gather_bands(Context& c, const int* edges, int8_t* grid, int W, int H, cudaStream_t st) {
   const int n = c.comm_nranks;
   if (n <= 1) return UQS_OK;
+  (void)H;
   ncclComm_t comm = (ncclComm_t)c.comm;
-  int r0, rows, first_rows = 0;
+  int r0, rows;
+  const int first_rows = edges[1] - edges[0];
   bool equal = true;
-  for (int r = 0; r < n; r++) {
-    uqs_row_band(H, r, n, 4, &r0, &rows);
-    if (r == 0) first_rows = rows;
-    equal = equal && rows == first_rows && r0 == r * first_rows;
-  }
+  for (int r = 0; r < n; r++) equal = equal && edges[r + 1] - edges[r] == first_rows;
   ncclResult_t q;
   if (equal) {
-    uqs_row_band(H, c.comm_rank, n, 4, &r0, &rows);
-    q = N.AllGather(grid + (size_t)r0 * W, grid, (size_t)rows * W, ncclInt8, comm, st);
+    r0 = edges[c.comm_rank];
+    q = N.AllGather(grid + (size_t)r0 * W, grid, (size_t)first_rows * W, ncclInt8, comm, st);
     return q == ncclSuccess ? UQS_OK : nccl_fail(q, "ncclAllGather(bands)");
   }
   if ((q = N.GroupStart()) != ncclSuccess) return nccl_fail(q, "ncclGroupStart");
   for (int r = 0; r < n; r++) {
-    uqs_row_band(H, r, n, 4, &r0, &rows);
+    r0 = edges[r];
+    rows = edges[r + 1] - edges[r];
     if (rows <= 0) continue;
     int8_t* band = grid + (size_t)r0 * W;
     if ((q = N.Broadcast(band, band, (size_t)rows * W, ncclInt8, r, comm, st)) != ncclSuccess) {
@@ -194,6 +256,30 @@ int uqs_comm_destroy(void) {
 }
 
 int uqs_comm_nranks(void) { return g_ctx.ready ? g_ctx.comm_nranks : 0; }
+
+/* The cuts uqs_replay_banded_dev would use for `world` ranks on this log (device pointers): edges_out[0..world]. */
+int uqs_balanced_row_bands_dev(const uqs_params* p, int n_frames, const float* x_dev, const float* y_dev, int world,
+                               int* edges_out) {
+  int rc = check_ready();
+  if (rc) return rc;
+  DevParams dp;
+  if ((rc = make_dev_params(p, &dp))) return rc;
+  if (n_frames <= 0 || !x_dev || !y_dev || world < 1 || world > kMaxDevices || !edges_out) { set_error("uqs_balanced_row_bands_dev: bad argument"); return UQS_ERR_BAD_ARG; }
+  return band_edges(dp, n_frames, x_dev, y_dev, world, 4, edges_out);
+}
+
+int uqs_set_band_balance(int on) {
+  g_balance = on != 0;
+  return UQS_OK;
+}
+
+/* edges_out[0..nranks]: the row cuts of the last banded replay on the current context (rank r owned rows
+ * [edges_out[r], edges_out[r+1])).  Returns the number of ranks. */
+int uqs_band_edges(int* edges_out) {
+  if (!g_ctx.ready || !edges_out) return 0;
+  for (int r = 0; r <= g_ctx.comm_nranks; r++) edges_out[r] = g_ctx.band_edges[r];
+  return g_ctx.comm_nranks;
+}
 int uqs_comm_rank(void) { return g_ctx.ready ? g_ctx.comm_rank : 0; }
 
 int uqs_nccl_version(void) {
@@ -213,10 +299,11 @@ int uqs_replay_banded_dev(const uqs_params* p, int n_frames, const float* x, con
   if ((rc = make_dev_params(p, &dp))) return rc;
   if (n_frames <= 0 || !x || !y || !yaw || !ranges || !grid) { set_error("uqs_replay_banded_dev: NULL pointer or non-positive size"); return UQS_ERR_BAD_ARG; }
   if (g_ctx.comm_nranks > 1 && !g_ctx.comm) { set_error("uqs_replay_banded_dev: no communicator (uqs_comm_init_rank)"); return UQS_ERR_NOT_INIT; }
-  int r0, rows;
-  uqs_row_band(p->H, g_ctx.comm_rank, g_ctx.comm_nranks, 4, &r0, &rows);
+  int* edges = g_ctx.band_edges;
+  if ((rc = band_edges(dp, n_frames, x, y, g_ctx.comm_nranks, 4, edges))) return rc;
+  const int r0 = edges[g_ctx.comm_rank], rows = edges[g_ctx.comm_rank + 1] - r0;
   if (rows > 0 && (rc = replay_device(dp, 1, n_frames, x, y, yaw, ranges, nullptr, grid, 0, r0, rows, true))) return rc;
-  if (gather && (rc = gather_bands(g_ctx, grid, p->W, p->H, g_ctx.stream()))) return rc;
+  if (gather && (rc = gather_bands(g_ctx, edges, grid, p->W, p->H, g_ctx.stream()))) return rc;
   // every rank's ray set-up sees the whole log, so the counters are the whole log's on every rank
   return rows > 0 ? fetch_stats(stats, (uint64_t)n_frames) : UQS_OK;
 }
@@ -370,12 +457,15 @@ int uqs_multi_replay_banded(const uqs_params* p, int n_frames, const float* x, c
     if (q != ncclSuccess) { N.GroupEnd(); return nccl_fail(q, "ncclAllGather(log)"); }
     if ((q = N.GroupEnd()) != ncclSuccess) return nccl_fail(q, "ncclGroupEnd");
   }
-  // 3. owned bands
+  // 3. owned bands (cuts from the log on device 0; the same on every device)
+  int edges[kMaxDevices + 1];
+  if ((rc = uqs_multi_select(0))) return rc;
+  if ((rc = band_edges(dp, n_frames, (float*)g_bands[0].x.p, (float*)g_bands[0].y.p, n, 4, edges))) return rc;
+  for (int i = 0; i < n; i++) memcpy(g_multi[i].band_edges, edges, sizeof(int) * (n + 1));
   for (int i = 0; i < n; i++) {
     if ((rc = uqs_multi_select(i))) return rc;
     BandBufs& B = g_bands[i];
-    int r0, rows;
-    uqs_row_band(p->H, i, n, 4, &r0, &rows);
+    const int r0 = edges[i], rows = edges[i + 1] - edges[i];
     if (rows > 0 && (rc = replay_device(dp, 1, n_frames, (float*)B.x.p, (float*)B.y.p, (float*)B.yaw.p, (float*)B.ranges.p, nullptr,
                                         (int8_t*)B.grid.p, 0, r0, rows, true)))
       return rc;
@@ -385,15 +475,14 @@ int uqs_multi_replay_banded(const uqs_params* p, int n_frames, const float* x, c
     ncclResult_t q = N.GroupStart();
     if (q != ncclSuccess) return nccl_fail(q, "ncclGroupStart");
     for (int i = 0; i < n; i++) {
-      if ((rc = gather_bands(g_multi[i], (int8_t*)g_bands[i].grid.p, p->W, p->H, g_multi[i].stream()))) { N.GroupEnd(); return rc; }
+      if ((rc = gather_bands(g_multi[i], edges, (int8_t*)g_bands[i].grid.p, p->W, p->H, g_multi[i].stream()))) { N.GroupEnd(); return rc; }
     }
     if ((q = N.GroupEnd()) != ncclSuccess) return nccl_fail(q, "ncclGroupEnd");
   }
   // 5. bands down, one link each
   for (int i = 0; i < n; i++) {
     if ((rc = uqs_multi_select(i))) return rc;
-    int r0, rows;
-    uqs_row_band(p->H, i, n, 4, &r0, &rows);
+    const int r0 = edges[i], rows = edges[i + 1] - edges[i];
     if (rows <= 0) continue;
     e = cudaMemcpyAsync(grid_out + (size_t)r0 * p->W, (int8_t*)g_bands[i].grid.p + (size_t)r0 * p->W, (size_t)rows * p->W,
                         cudaMemcpyDeviceToHost, g_ctx.stream());

@@ -119,6 +119,18 @@ def test_c4_full_building_sweep_row_bands(gpu, oracle, synth, torch_stream):
         _replay(gpu, p, 1, N, t, g2, row0=r0, rows=rows)
     torch.cuda.synchronize()
     assert torch.equal(g1, g2), "union of owned row bands differs from the whole grid"
+    # the balanced cuts of a 2/4/8-rank run (equal shares of the log, not of the rows): same union, and every band carries work
+    for world in (2, 4, 8):
+        edges = gpu.balanced_row_bands_dev(p, N, t[0].data_ptr(), t[1].data_ptr(), world)
+        assert edges[0] == 0 and edges[-1] == p.H and all(b > a and a % 4 == 0 for a, b in zip(edges, edges[1:]))
+        if world == 8:
+            equal = [sh.row_band(p.H, r, 8)[0] for r in range(8)] + [p.H]
+            assert edges != equal                          # the sweep covers the middle of the grid: equal bands are not balanced
+            g2.fill_(9)
+            for a, b in zip(edges, edges[1:]):
+                _replay(gpu, p, 1, N, t, g2, row0=a, rows=b - a)
+            torch.cuda.synchronize()
+            assert torch.equal(g1, g2), "union of balanced row bands differs from the whole grid"
     # oracle on an 8 000-frame prefix
     n = 8000
     g3 = torch.empty_like(g1)
