@@ -121,8 +121,8 @@ int  uqs_sync(void);
  * (1 = never slice).  Any setting produces identical bytes. */
 int  uqs_set_tuning(int subtile_w, int subtile_h, int time_slices);
 /* Replay engine: 0 = automatic (each flight's touched bounding box resident in one CTA's
- * shared memory when several such CTAs fit an SM and there is at least one flight per
- * SM; warp-owned sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
+ * shared memory when it fits and there are at least SMs/4 flights; warp-owned
+ * sub-tiles otherwise), 1 = always sub-tiles, 2 = always resident
  * (error if the flights' touched bounding box does not fit), 3 = always the unrestricted
  * kernel.  flight_warps = warps per CTA of the resident engine (0 = automatic, 4, 8, 16
  * or 32).  All engines produce identical bytes.

@@ -346,12 +346,15 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         set_error("engine 2: the touched region %dx%d of a flight does not fit %zu B of shared memory", bw, bh, kFlightSmemMax);
         return UQS_ERR_BAD_ARG;
       }
-      // auto: resident when the box fits and there is at least a flight per SM (measured crossover; with one CTA of
+      // auto: resident when the box fits and there are at least SMs/4 flights (measured crossover; with one CTA of
       // 16 warps per SM it still beats the sub-tile engine by 1.6x on the 668^2 and 800^2 grids of config 5);
       // otherwise the sub-tile engine (time-sliced when flights are few)
       // (a chunk of the host-buffer pipeline shares the chip with its neighbours: no flight-count condition there)
+      // (round 2, tools/c5_shard_engines.py: with 128 flights -- a 1/8 shard of a config-5 resolution -- the resident engine
+      // at 16 warps per CTA needs 1.8-2.8 ms against 3.3-6.9 ms for time-sliced sub-tiles on every geometry that fits; one
+      // resident flight takes ~2 ms whatever the count, the sub-tile engine ~0.9 ms + 0.04 ms per flight: crossover ~30)
       const bool pipelined = g_ctx.chip_shared;               // other chunks of a host-buffer call share the chip
-      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || nf >= g_ctx.sm_count || pipelined);
+      const bool resident = f_ctas >= 1 && (g_ctx.engine == 2 || nf * 4 >= g_ctx.sm_count || pipelined);
       if (resident) {
         FlightArgs FA;
         FA.frames = (const uint4*)g_ctx.w->frames.p;
