@@ -583,9 +583,9 @@ def run_c4(cx, verify_n1):
     torch.cuda.synchronize()
     steps, warmup = max(2, min(args.steps, 3)), 2
 
-    def step_device(want_stats=False):
+    def step_device(want_stats=False, gather=True):
         return m.replay_banded_dev(p, NF, dv["x"].data_ptr(), dv["y"].data_ptr(), dv["yaw"].data_ptr(), dv["ranges"].data_ptr(),
-                                   grid.data_ptr(), gather=True, want_stats=want_stats)
+                                   grid.data_ptr(), gather=gather, want_stats=want_stats)
 
     def step_e2e():
         m.replay_banded(p, hp["x"].numpy(), hp["y"].numpy(), hp["yaw"].numpy(), hp["ranges"].numpy(),
@@ -602,12 +602,21 @@ def run_c4(cx, verify_n1):
     launches = m.kernel_launches() - l0
     kms, _ = m.profile_collect()
     m.set_profiling(False)
+    # the same step without the exchange (what the NCCL gather of the bands costs), and every rank's own kernel time
+    ms_nogather = cx.timed(lambda: step_device(gather=False), steps, 0) if cx.world > 1 else ms
+    per_rank = [0.0] * cx.world
+    per_rank[cx.rank] = (kms[1] + kms[2]) / steps
+    if cx.world > 1:
+        tr = torch.tensor(per_rank, dtype=torch.float64, device=cx.dev)
+        cx.dist.all_reduce(tr)
+        per_rank = tr.tolist()
     edges = m.band_edges()
     hh = int(m.grid_hashes_dev(grid.data_ptr(), 1, p.W * p.H)[0])
     rec = {"workload": f"BASELINE config 4: {w.name}", "samples": w.n_samples, "frames": NF, "beams_per_sample": 64,
            "grid": f"{p.W}x{p.H}", "value": U / (ms * 1e-3), "unit": "updates/s", "ms_per_step": ms, "updates": U,
            "frames_per_s": NF / (ms * 1e-3), "steps": steps, "warmup": warmup,
            "kernel_ms_rank0": {"ray_setup": kms[1] / steps, "replay": kms[2] / steps},
+           "kernel_ms_per_rank": [round(v, 3) for v in per_rank], "ms_per_step_without_gather": ms_nogather,
            "partition": f"{cx.world} owned row bands cut at rows {edges} (equal shares of the log: origin-row histogram widened by the "
                         "sensor's reach, computed on the device every call)", "exchange": "one ncclAllGather of the bands inside libuqs_mapping, in the timed region",
            "comm_nranks_seen": [m.comm_nranks()], "nccl_version": m.nccl_version() if cx.world > 1 else None,

@@ -199,6 +199,15 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     const long long jobs80 = (long long)n_flights * nsx * nsy;
     int want = g_ctx.tune_slices;
     int slice_tile = 40;
+    const bool band = rows < dp.H;          // an owned row band of a grid shared between GPUs
+    if (want == 0 && band && g_ctx.tune_sw == 0 && g_ctx.tune_sh == 0 && jobs80 < 2 * warp_slots) {
+      // A band holds too few 80x100 tiles to balance the persistent warps, but time slices do not pay here: the band's
+      // hot tiles already bound the launch (one warp per tile job, ~6 ms for a tile the sweep passes twice), and map
+      // tiles cost 3x the instructions per update.  Measured per band of the 16384^2 sweep cut 8 / 4 / 2 ways
+      // (tools/c4_band_tuning.py, profiles/r2_c4_band_tuning.log): 56-cell value tiles, no slices.
+      choose_tiles(dp.W, rows, 56, &sw, &sh, &nsx, &nsy);
+      want = 1;
+    }
     if (want == 0 && jobs80 < 2 * warp_slots) {
       // largest map tile that still yields >= 8 jobs per warp slot at the finest admissible slicing (>= 256
       // frames per slice, <= 64 slices).  Measured: 56-cell tiles win for long rays (>= 200 cells: the one-hour
