@@ -137,6 +137,9 @@ int  uqs_set_engine(int engine, int flight_warps);
  * instruction, 1 = the 8 beams of one sensor x 4 consecutive steps (fewer shared-memory bank conflicts).
  * -1 = the built-in choice.  Identical bytes either way. */
 int  uqs_set_fan_layout(int on);
+/* Experiment knob for the layouts above: row pitch of the resident box in 32-bit words, modulo 32
+ * (-1 = the built-in odd pitch).  Identical bytes for any value. */
+int  uqs_set_resident_pitch_mod(int words_mod32);
 
 /*
  * P0 -- dead-reckoning pose integration (BUILDER-DEFINED: the reference has no

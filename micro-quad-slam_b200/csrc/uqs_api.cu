@@ -322,6 +322,8 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
       const int bw = std::max(dims[0], 4), bh = std::max(dims[1], 1);
       int fpitch = (bw + 3) & ~3;
       if (((fpitch >> 2) & 1) == 0) fpitch += 4;
+      if (g_ctx.pitch_mod >= 0)                                 // experiment knob: row pitch in words == pitch_mod (mod 32)
+        while (((fpitch >> 2) & 31) != g_ctx.pitch_mod) fpitch += 4;
       const size_t region = (size_t)fpitch * bh;
       // Warps per resident CTA.  Measured over box sizes from 17 KB (8 CTAs per SM) to 173 KB (one): the kernel wants
       // >= 24 resident warps per SM from as few warps per CTA as possible (per-frame work is paid per warp), and never
@@ -647,6 +649,12 @@ int uqs_set_engine(int engine, int flight_warps) {
 
 /* Lane layout of the resident engine's free-space steps: 0 = 32 beams x 1 step, 1 = 8 beams of one sensor x 4
  * consecutive steps (see k_replay_flights).  Identical bytes. */
+/* Experiment knob: row pitch of the resident box in 32-bit words, modulo 32 (-1 = the built-in odd pitch). */
+int uqs_set_resident_pitch_mod(int words_mod32) {
+  g_ctx.pitch_mod = words_mod32 < 0 ? -1 : (words_mod32 & 31);
+  return UQS_OK;
+}
+
 int uqs_set_fan_layout(int on) {
   g_ctx.flight_fan = on < 0 ? kDefaultFanLayout : (on ? 1 : 0);
   return UQS_OK;

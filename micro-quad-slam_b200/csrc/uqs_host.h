@@ -48,6 +48,7 @@ struct Context {
   int tune_sw = 0, tune_sh = 0, tune_slices = 0;
   int engine = 0;                               // 0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA
   int flight_warps = 0;                         // warps per CTA of the resident engine (0 = 16)
+  int pitch_mod = -1;                           // experiment: resident row pitch in words mod 32 (uqs_set_resident_pitch_mod)
   int flight_fan = kDefaultFanLayout;           // lane layout of its free-space steps (uqs_set_fan_layout)
   int host_chunk = 0;                           // flights per chunk of the host-buffer pipeline (0 = auto)
   bool copy_only = false;                       // measurement: host-buffer calls skip their kernels (uqs_set_copy_only)
