@@ -154,6 +154,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
                   int accumulate, int row0, int rows, bool reset_stats) {
   cudaStream_t st = g_ctx.stream();
   const int gpf = (n_frames + 31) / 32;
+  g_ctx.w->boxes_valid = false;                  // set again below once this call's touched boxes exist
   {
     const int rc0 = ensure_inv_table();
     if (rc0) return rc0;
@@ -279,7 +280,6 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     if (e != cudaSuccess) return cuda_fail(e, "memset stats");
   }
 
-  g_ctx.w->boxes_valid = false;
   int ctas_per_sm = 0;
   e = cudaFuncSetAttribute(k_replay_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_replay_tiles)");

@@ -39,6 +39,8 @@ struct Nccl {
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -62,6 +64,8 @@ int nccl_load() {
   N.CommDestroy = (decltype(N.CommDestroy))sym("ncclCommDestroy");
   N.AllGather = (decltype(N.AllGather))sym("ncclAllGather");
   N.Broadcast = (decltype(N.Broadcast))sym("ncclBroadcast");
+  N.Send = (decltype(N.Send))sym("ncclSend");
+  N.Recv = (decltype(N.Recv))sym("ncclRecv");
   N.GroupStart = (decltype(N.GroupStart))sym("ncclGroupStart");
   N.GroupEnd = (decltype(N.GroupEnd))sym("ncclGroupEnd");
   N.GetErrorString = (decltype(N.GetErrorString))sym("ncclGetErrorString");
@@ -158,7 +162,7 @@ void comm_release() {
 }
 
 // Gather the owned row bands of `grid` (full W*H on every rank, band r valid on rank r) so that every rank holds
-// the whole grid.  In place; equal bands: one ncclAllGather, ragged: one grouped ncclBroadcast per band.
+// the whole grid.  In place; equal bands: one ncclAllGather, ragged: grouped ncclSend/ncclRecv between all pairs.
 static int gather_bands(Context& c, const int* edges, int8_t* grid, int W, int H, cudaStream_t st) {
   const int n = c.comm_nranks;
   if (n <= 1) return UQS_OK;
@@ -174,16 +178,21 @@ static int gather_bands(Context& c, const int* edges, int8_t* grid, int W, int H
     q = N.AllGather(grid + (size_t)r0 * W, grid, (size_t)first_rows * W, ncclInt8, comm, st);
     return q == ncclSuccess ? UQS_OK : nccl_fail(q, "ncclAllGather(bands)");
   }
+  // ragged bands: every rank sends its band to every peer and receives theirs, all in one group (the transfers run
+  // concurrently over NVSwitch; eight back-to-back broadcasts of the same bytes took 2.5 ms for 268 MB on 8 GPUs)
   if ((q = N.GroupStart()) != ncclSuccess) return nccl_fail(q, "ncclGroupStart");
-  for (int r = 0; r < n; r++) {
+  const int me = c.comm_rank;
+  const int my0 = edges[me], my_rows = edges[me + 1] - edges[me];
+  for (int r = 0; r < n && q == ncclSuccess; r++) {
+    if (r == me) continue;
     r0 = edges[r];
     rows = edges[r + 1] - edges[r];
-    if (rows <= 0) continue;
-    int8_t* band = grid + (size_t)r0 * W;
-    if ((q = N.Broadcast(band, band, (size_t)rows * W, ncclInt8, r, comm, st)) != ncclSuccess) {
-      N.GroupEnd();
-      return nccl_fail(q, "ncclBroadcast(band)");
-    }
+    if (my_rows > 0) q = N.Send(grid + (size_t)my0 * W, (size_t)my_rows * W, ncclInt8, r, comm, st);
+    if (q == ncclSuccess && rows > 0) q = N.Recv(grid + (size_t)r0 * W, (size_t)rows * W, ncclInt8, r, comm, st);
+  }
+  if (q != ncclSuccess) {
+    N.GroupEnd();
+    return nccl_fail(q, "ncclSend/ncclRecv(band)");
   }
   q = N.GroupEnd();
   return q == ncclSuccess ? UQS_OK : nccl_fail(q, "ncclGroupEnd");
