@@ -75,3 +75,24 @@ def test_millimetre_form_of_the_synthetic_ranges_is_lossless(synth):
     assert not np.array_equal(synth.mm_to_ranges(synth.ranges_to_mm(d0["ranges"])).view(np.uint32), d0["ranges"].view(np.uint32))
     # everything but the ranges is the same log
     assert np.array_equal(d0["of_rate_x"], d["of_rate_x"]) and np.array_equal(d0["yaw_deg"], d["yaw_deg"])
+
+
+def test_bench_digest_of_a_sharded_job_is_the_digest_of_the_whole_job():
+    """bench.py reduces per-rank digests with a sum mod 2^64 (hash) and compares with the same job on one GPU
+    (hash_n1): the combination must not depend on how the grids are split over ranks."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(9)
+    h = rng.integers(0, 2 ** 63, 1000, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    whole = bench.combine_hashes(h, 0)
+    for cuts in ((0, 500, 1000), (0, 1, 999, 1000), (0, 125, 250, 375, 500, 625, 750, 875, 1000)):
+        parts = sum(bench.combine_hashes(h[a:b], a) for a, b in zip(cuts, cuts[1:])) & bench.M64
+        assert parts == whole
+    assert bench.combine_hashes(h[::-1].copy(), 0) != whole          # which grid belongs to which flight matters
+    # the four 16-bit limbs an int64 all-reduce carries reassemble the sum exactly
+    vals = [int(v) for v in h[:8]]
+    limbs = [sum((v >> (16 * i)) & 0xFFFF for v in vals) for i in range(4)]
+    assert sum(l << (16 * i) for i, l in enumerate(limbs)) & bench.M64 == sum(vals) & bench.M64
