@@ -765,6 +765,62 @@ def test_dropin_symbols_replay_like_log_tick(gpu, oracle, orc_mod, synth):
         assert np.array_equal(got, ref.grid())
 
 
+def test_dropin_symbols_on_a_grid_wider_than_1025_cells(gpu, oracle):
+    """raycast_update() takes arbitrary end points: on a grid wider than 1025 cells a single call may be a ray of more
+    than 1024 cells, so the drop-in queue is replayed by the unrestricted kernel (raw-ray entries included); an
+    edited occ_grid with values outside [-80, 80] is honoured the way the reference's clamp does."""
+    p = gpu.make_params(1400, 1200, 0.01, 14.0)
+    di = gpu.DropIn(p)
+    di.hover_init(0.5, -0.25)
+    q = p.copy()
+    q.origin_x, q.origin_y = np.float32(0.5), np.float32(-0.25)
+    want = np.zeros((p.H, p.W), np.int8)
+    rng = np.random.default_rng(77)
+    for i in range(120):
+        x, y, yaw = (np.float32(v) for v in (0.5 + rng.uniform(-2, 2), -0.25 + rng.uniform(-2, 2), rng.uniform(-180, 180)))
+        beams = rng.uniform(0.03, 4.4, 32).astype(np.float32)
+        beams[rng.random(32) < 0.1] = np.nan
+        di.set_beams(beams)
+        di.map_update_from_beams(x, y, yaw)
+        oracle.L.orc_frame(ctypes.byref(q), want.ctypes.data, x, y, yaw, np.ascontiguousarray(beams).ctypes.data)
+        if i % 10 == 0:
+            a = (float(x), float(y), float(np.float32(0.5 + rng.uniform(-6.9, 6.9))), float(np.float32(-0.25 + rng.uniform(-5.9, 5.9))))
+            hit = bool(i % 20)
+            di.raycast_update(*a, hit)                 # up to ~1380 cells long
+            oracle.raycast(q, want, *a, hit)
+    got = di.grid()
+    assert np.array_equal(got, want), first_diff(got, want)
+    assert (want != 0).sum() > 20000
+
+
+def test_unrestricted_kernel_with_row_bands_and_chained_replays(gpu, oracle, synth):
+    import torch
+    w = synth.scaled(synth.CONFIGS["c3"], n_flights=3, n_samples=400)
+    d = synth.generate(w)
+    p = w.params()
+    want, _ = oracle_grids(oracle, p, d)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (d["x_true"], d["y_true"], d["frame_yaw_deg"], d["ranges"])]
+    g = torch.full((3, p.H, p.W), 7, dtype=torch.int8, device=dev)
+    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    gpu.set_engine(3, 0)
+    try:
+        for r0, rows in ((0, 120), (120, 164), (284, 116)):                                 # three owned bands, fresh
+            gpu.replay_dev(p, 3, 400, *(a.data_ptr() for a in t), g.data_ptr(), row0=r0, rows=rows)
+        torch.cuda.synchronize()
+        assert np.array_equal(g.cpu().numpy(), want)
+        g.zero_()
+        h = 173
+        gpu.replay_dev(p, 3, h, *(a[:, :h].contiguous().data_ptr() for a in t), g.data_ptr(), accumulate=True)
+        t2 = [a[:, h:].contiguous() for a in t]
+        gpu.replay_dev(p, 3, 400 - h, *(a.data_ptr() for a in t2), g.data_ptr(), accumulate=True)   # chained halves
+        torch.cuda.synchronize()
+        assert np.array_equal(g.cpu().numpy(), want)
+    finally:
+        gpu.set_engine(0, 0)
+        gpu.set_stream(None)
+
+
 # ----------------------------------------------------------------------------------------------
 # randomized stress: odd geometries and sensor constants against the oracle, every engine
 # ----------------------------------------------------------------------------------------------
