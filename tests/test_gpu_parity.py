@@ -811,7 +811,8 @@ def test_unrestricted_kernel_with_row_bands_and_chained_replays(gpu, oracle, syn
         assert np.array_equal(g.cpu().numpy(), want)
         g.zero_()
         h = 173
-        gpu.replay_dev(p, 3, h, *(a[:, :h].contiguous().data_ptr() for a in t), g.data_ptr(), accumulate=True)
+        t1 = [a[:, :h].contiguous() for a in t]                                             # kept alive until the sync
+        gpu.replay_dev(p, 3, h, *(a.data_ptr() for a in t1), g.data_ptr(), accumulate=True)
         t2 = [a[:, h:].contiguous() for a in t]
         gpu.replay_dev(p, 3, 400 - h, *(a.data_ptr() for a in t2), g.data_ptr(), accumulate=True)   # chained halves
         torch.cuda.synchronize()
