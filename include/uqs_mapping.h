@@ -137,6 +137,10 @@ int  uqs_set_engine(int engine, int flight_warps);
  * instruction, 1 = the 8 beams of one sensor x 4 consecutive steps (fewer shared-memory bank conflicts).
  * -1 = the built-in choice.  Identical bytes either way. */
 int  uqs_set_fan_layout(int on);
+/* Resident engine with a dedicated decode warp: 0 = every warp decodes every NW-th frame of its flight, 1 = an
+ * extra producer warp per CTA does nothing but decode frames into the shared-memory ring, two frames ahead of the
+ * consumer warps (4, 8 or 16 of them).  -1 = the built-in choice.  Identical bytes either way. */
+int  uqs_set_decode_warp(int on);
 /* Experiment knob for the layouts above: row pitch of the resident box in 32-bit words, modulo 32
  * (-1 = the built-in odd pitch).  Identical bytes for any value. */
 int  uqs_set_resident_pitch_mod(int words_mod32);

@@ -336,7 +336,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         while (*ring > 32 && region + (size_t)(*ring + 4) * w + dec_bytes > kFlightSmemMax) *ring >>= 1;
         *bytes = region + (size_t)(*ring + 4) * w + dec_bytes;         // + one spare word per warp
         *ctas = 0;
-        return *bytes <= kFlightSmemMax ? flights_prepare(w, g_ctx.flight_fan, *bytes, ctas) : cudaSuccess;
+        return *bytes <= kFlightSmemMax ? flights_prepare(w, g_ctx.flight_fan, g_ctx.flight_prod, *bytes, ctas) : cudaSuccess;
       };
       if (g_ctx.flight_warps) {
         e = fit(fnw, &ring_size, &fsmem, &f_ctas);
@@ -384,7 +384,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
         if (e != cudaSuccess) return cuda_fail(e, "memset before k_replay_flights");
         const unsigned fgrid = (unsigned)std::min<long long>(nf, (long long)f_ctas * g_ctx.sm_count);
         KernelTimer t_rep(2);
-        e = flights_launch(fnw, g_ctx.flight_fan, fgrid, fsmem, st, FA);
+        e = flights_launch(fnw, g_ctx.flight_fan, g_ctx.flight_prod, fgrid, fsmem, st, FA);
         t_rep.stop();
         if (e != cudaSuccess) return cuda_fail(e, "k_replay_flights launch");
         g_ctx.launches += 2;
@@ -651,6 +651,13 @@ int uqs_set_engine(int engine, int flight_warps) {
 /* Experiment knob: row pitch of the resident box in 32-bit words, modulo 32 (-1 = the built-in odd pitch). */
 int uqs_set_resident_pitch_mod(int words_mod32) {
   g_ctx.pitch_mod = words_mod32 < 0 ? -1 : (words_mod32 & 31);
+  return UQS_OK;
+}
+
+/* Resident engine with a dedicated decode warp (0 = every warp decodes every NW-th frame, 1 = an extra producer warp;
+ * -1 = the built-in choice).  Identical bytes. */
+int uqs_set_decode_warp(int on) {
+  g_ctx.flight_prod = on < 0 ? kDefaultDecodeWarp : (on ? 1 : 0);
   return UQS_OK;
 }
 

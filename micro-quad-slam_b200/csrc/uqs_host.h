@@ -10,6 +10,7 @@
 
 namespace uqs {
 
+constexpr int kDefaultDecodeWarp = 0;           // resident engine: 1 = an extra warp per CTA that only decodes (measured choice)
 constexpr int kDefaultFanLayout = 0;            // resident engine: 0 = 32 beams x 1 step, 1 = 8 beams x 4 steps (measured choice)
 
 // grow-only device buffer
@@ -49,6 +50,7 @@ struct Context {
   int engine = 0;                               // 0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA
   int flight_warps = 0;                         // warps per CTA of the resident engine (0 = 16)
   int pitch_mod = -1;                           // experiment: resident row pitch in words mod 32 (uqs_set_resident_pitch_mod)
+  int flight_prod = kDefaultDecodeWarp;         // dedicated decode warp (uqs_set_decode_warp)
   int flight_fan = kDefaultFanLayout;           // lane layout of its free-space steps (uqs_set_fan_layout)
   int host_chunk = 0;                           // flights per chunk of the host-buffer pipeline (0 = auto)
   bool copy_only = false;                       // measurement: host-buffer calls skip their kernels (uqs_set_copy_only)

@@ -902,9 +902,13 @@ __device__ __forceinline__ Beam decode_beam(uint2 rec, uint2 org, int P, int bx0
 // 32-beam layout conflict), and the lanes are fuller (25 of 32 instead of 22.7: a short fan no longer idles its lanes
 // through the long fans' steps).  Same cells, same order constraints: every (beam, step >= K0) cell of a frame is
 // touched by exactly one lane, whichever layout enumerates them.
-template <int NW, int FAN>
-__global__ void __launch_bounds__(NW * 32, (NW <= 4) ? UQS_MINB : ((NW <= 8) ? 4 : ((NW <= 16) ? 2 : 1)))
+// PROD = 1: warp specialisation -- an extra (NW+1)-th warp does nothing but decode frames into the ring, two frames
+// ahead of the NW consumer warps, and joins the per-frame barrier; the consumers never decode or load raw records.
+template <int NW, int FAN, int PROD>
+__global__ void __launch_bounds__((NW + PROD) * 32, (NW <= 4) ? (PROD ? 6 : UQS_MINB) : ((NW <= 8) ? 4 : ((NW <= 16) ? 2 : 1)))
 k_replay_flights(FlightArgs A) {
+  constexpr int NT = (NW + PROD) * 32;          // threads per CTA
+  const bool producer = PROD && (threadIdx.x >> 5) == NW;
   int8_t* grid_s = reinterpret_cast<int8_t*>(uqs_smem);
   __shared__ int s_flight;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -941,18 +945,18 @@ k_replay_flights(FlightArgs A) {
     if (A.accumulate) {
       if (vec) {
         const int wpr = bw >> 2;
-        for (int i = threadIdx.x; i < wpr * bh; i += NW * 32) {
+        for (int i = threadIdx.x; i < wpr * bh; i += NT) {
           const int r = i / wpr, c = i - r * wpr;
           reinterpret_cast<uint32_t*>(grid_s + r * P)[c] = reinterpret_cast<const uint32_t*>(grid_g + (size_t)r * A.W)[c];
         }
       } else {
-        for (int i = threadIdx.x; i < bw * bh; i += NW * 32) {
+        for (int i = threadIdx.x; i < bw * bh; i += NT) {
           const int r = i / bw, c = i - r * bw;
           grid_s[r * P + c] = grid_g[(size_t)r * A.W + c];
         }
       }
     } else {
-      for (int i = threadIdx.x; i < ((P * bh) >> 2); i += NW * 32) reinterpret_cast<uint32_t*>(grid_s)[i] = 0u;
+      for (int i = threadIdx.x; i < ((P * bh) >> 2); i += NT) reinterpret_cast<uint32_t*>(grid_s)[i] = 0u;
     }
     __syncthreads();
 
@@ -980,17 +984,34 @@ k_replay_flights(FlightArgs A) {
                                                    ((uint32_t)b.end_delta & 0xffu));
       if (lane == 0) sts_v4(at + 1024u, (uint32_t)b.base, (uint32_t)b.k0, (uint32_t)mx, (org.y & kFrameSorted) ? 1u : 0u);
     };
-    if (w < L && w < A.n_frames)
-      decode_store(__ldg(&rays[(size_t)w * 32 + lane]), __ldg(reinterpret_cast<const uint2*>(&frames[w])), w);
-    // raw records of this warp's next turn (frame w + L), loaded one turn (NW frames) ahead
     uint2 raw_rec, raw_org;
-    {
+    if (PROD) {
+      if (producer) {                              // the first L frames, then the records of frame L
+        for (int g = 0; g < L && g < A.n_frames; g++)
+          decode_store(__ldg(&rays[(size_t)g * 32 + lane]), __ldg(reinterpret_cast<const uint2*>(&frames[g])), g);
+        const int g = min(L, A.n_frames - 1);
+        raw_rec = __ldg(&rays[(size_t)g * 32 + lane]);
+        raw_org = __ldg(reinterpret_cast<const uint2*>(&frames[g]));
+      }
+    } else {
+      if (w < L && w < A.n_frames)
+        decode_store(__ldg(&rays[(size_t)w * 32 + lane]), __ldg(reinterpret_cast<const uint2*>(&frames[w])), w);
+      // raw records of this warp's next turn (frame w + L), loaded one turn (NW frames) ahead
       const int g = min(w + L, A.n_frames - 1);
       raw_rec = __ldg(&rays[(size_t)g * 32 + lane]);
       raw_org = __ldg(reinterpret_cast<const uint2*>(&frames[g]));
     }
     __syncthreads();
     for (int f = 0; f < A.n_frames; f++) {
+      if (producer) {                              // decode frame f + L while the consumers work on frame f
+        const int g = f + L;
+        if (g < A.n_frames) decode_store(raw_rec, raw_org, g & (R - 1));
+        const int gn = min(g + 1, A.n_frames - 1);
+        raw_rec = __ldg(&rays[(size_t)gn * 32 + lane]);
+        raw_org = __ldg(reinterpret_cast<const uint2*>(&frames[gn]));
+        __syncthreads();
+        continue;
+      }
       const uint32_t at = dec_sa + (uint32_t)(f & (R - 1)) * kDecSlotBytes;
       UQS_CHECK(at + 16u * (uint32_t)lane, 16u, RD); UQS_CHECK(at + 1024u, 16u, RD);
       const uint4 fv = lds_v4(at + 1024u);
@@ -1197,7 +1218,7 @@ k_replay_flights(FlightArgs A) {
         }
       }
       }   // !FAN
-      if ((f & (NW - 1)) == w) {                    // this warp's turn: decode frame f + L, prefetch its next turn
+      if (!PROD && (f & (NW - 1)) == w) {           // this warp's turn: decode frame f + L, prefetch its next turn
         const int g = f + L;
         if (g < A.n_frames) decode_store(raw_rec, raw_org, g & (R - 1));
         const int gn = min(g + NW, A.n_frames - 1);
@@ -1209,12 +1230,12 @@ k_replay_flights(FlightArgs A) {
 
     if (vec) {
       const int wpr = bw >> 2;
-      for (int i = threadIdx.x; i < wpr * bh; i += NW * 32) {
+      for (int i = threadIdx.x; i < wpr * bh; i += NT) {
         const int r = i / wpr, c = i - r * wpr;
         reinterpret_cast<uint32_t*>(grid_g + (size_t)r * A.W)[c] = reinterpret_cast<const uint32_t*>(grid_s + r * P)[c];
       }
     } else {
-      for (int i = threadIdx.x; i < bw * bh; i += NW * 32) {
+      for (int i = threadIdx.x; i < bw * bh; i += NT) {
         const int r = i / bw, c = i - r * bw;
         grid_g[(size_t)r * A.W + c] = grid_s[r * P + c];
       }
@@ -1251,9 +1272,10 @@ __global__ void k_flight_boxes(int n_flights, int groups_per_flight, const uint2
   }
 }
 
-static void (*flight_kernel(int nw, int fan))(FlightArgs) {
-  if (fan) return nw == 4 ? k_replay_flights<4, 1> : (nw == 8 ? k_replay_flights<8, 1> : (nw == 32 ? k_replay_flights<32, 1> : k_replay_flights<16, 1>));
-  return nw == 4 ? k_replay_flights<4, 0> : (nw == 8 ? k_replay_flights<8, 0> : (nw == 32 ? k_replay_flights<32, 0> : k_replay_flights<16, 0>));
+static void (*flight_kernel(int nw, int fan, int prod))(FlightArgs) {
+  if (prod) return nw == 4 ? k_replay_flights<4, 0, 1> : (nw == 8 ? k_replay_flights<8, 0, 1> : (nw == 32 ? k_replay_flights<16, 0, 1> : k_replay_flights<16, 0, 1>));
+  if (fan) return nw == 4 ? k_replay_flights<4, 1, 0> : (nw == 8 ? k_replay_flights<8, 1, 0> : (nw == 32 ? k_replay_flights<32, 1, 0> : k_replay_flights<16, 1, 0>));
+  return nw == 4 ? k_replay_flights<4, 0, 0> : (nw == 8 ? k_replay_flights<8, 0, 0> : (nw == 32 ? k_replay_flights<32, 0, 0> : k_replay_flights<16, 0, 0>));
 }
 
 // dims -> mapped host memory: a device-to-host memcpy of these two words would queue on the D2H copy engine
@@ -1271,14 +1293,17 @@ cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint
   return cudaGetLastError();
 }
 
-cudaError_t flights_prepare(int nw, int fan, size_t smem, int* ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(flight_kernel(nw, fan), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// (the producer variant exists for 4, 8 and 16 consumer warps; 32 + 1 warps would exceed a CTA)
+static int flight_threads(int nw, int prod) { return (std::min(nw, prod ? 16 : 32) + (prod ? 1 : 0)) * 32; }
+
+cudaError_t flights_prepare(int nw, int fan, int prod, size_t smem, int* ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(flight_kernel(nw, fan, prod), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, flight_kernel(nw, fan), nw * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, flight_kernel(nw, fan, prod), flight_threads(nw, prod), smem);
 }
 
-cudaError_t flights_launch(int nw, int fan, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A) {
-  flight_kernel(nw, fan)<<<grid, nw * 32, smem, st>>>(A);
+cudaError_t flights_launch(int nw, int fan, int prod, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A) {
+  flight_kernel(nw, fan, prod)<<<grid, flight_threads(nw, prod), smem, st>>>(A);
   return cudaGetLastError();
 }
 

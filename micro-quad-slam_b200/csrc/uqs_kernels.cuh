@@ -77,8 +77,8 @@ __global__ void k_compose_slices(int8_t* grids, const uint32_t* maps, int n_flig
                                  int rows);
 cudaError_t flight_boxes_launch(int n_flights, int groups_per_flight, const uint2* groups, int W, int H, int4* boxes,
                                 int* dims, int* host_dims_dev, cudaStream_t st);
-cudaError_t flights_prepare(int nw, int fan, size_t smem, int* ctas_per_sm);
-cudaError_t flights_launch(int nw, int fan, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
+cudaError_t flights_prepare(int nw, int fan, int prod, size_t smem, int* ctas_per_sm);
+cudaError_t flights_launch(int nw, int fan, int prod, unsigned grid, size_t smem, cudaStream_t st, const FlightArgs& A);
 __global__ void k_rmw_peak(int tile_bytes, int iters, int lo_min, int* sink);
 __global__ void k_atoms_peak(int tile_bytes, int iters, int* sink);
 // uqs_next.cu

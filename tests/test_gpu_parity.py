@@ -12,17 +12,20 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(params=["tiles", "resident4", "resident8", "resident16", "resident32", "resident4fan", "resident8fan", "resident16fan",
-                        "resident32fan"])
+                        "resident32fan", "resident4dec", "resident8dec", "resident16dec"])
 def engine(request, gpu):
-    """Both replay engines (the resident engine's warp counts and both of its lane layouts) must give identical bytes."""
+    """Both replay engines (the resident engine's warp counts, both of its lane layouts, shared or dedicated decode
+    warp) must give identical bytes."""
     name = request.param
-    fan = name.endswith("fan")
-    e, nw = {"tiles": (1, 0), "resident4": (2, 4), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[name[:-3] if fan else name]
+    fan, dec = name.endswith("fan"), name.endswith("dec")
+    e, nw = {"tiles": (1, 0), "resident4": (2, 4), "resident8": (2, 8), "resident16": (2, 16), "resident32": (2, 32)}[name[:-3] if fan or dec else name]
     gpu.set_engine(e, nw)
     gpu.set_fan_layout(1 if fan else 0)
+    gpu.set_decode_warp(1 if dec else 0)
     yield name
     gpu.set_engine(0, 0)
     gpu.set_fan_layout(-1)
+    gpu.set_decode_warp(-1)
 
 
 def oracle_grids(oracle, p, d, x=None, y=None):
@@ -861,11 +864,12 @@ def test_random_geometry_and_sensor_constants(gpu, oracle, seed):
     want, U = oracle.replay_flights(p, x, y, yaw, r)
     cases = [(1, 0, 1, 0), (1, 0, 3, 0), (0, 0, 0, 0)]
     if max(W, H) <= 400:
-        cases += [(2, 4, 0, 0), (2, 16, 0, 0), (2, 4, 0, 1), (2, 8, 0, 1), (2, 32, 0, 1)]
+        cases += [(2, 4, 0, 0), (2, 16, 0, 0), (2, 4, 0, 1), (2, 8, 0, 1), (2, 32, 0, 1), (2, 4, 0, 2), (2, 8, 0, 2), (2, 16, 0, 2)]
     try:
-        for engine, nw, slices, fan in cases:
+        for engine, nw, slices, fan in cases:                      # fan: 0 = 32-beam layout, 1 = fan layout, 2 = dedicated decode warp
             gpu.set_engine(engine, nw)
-            gpu.set_fan_layout(fan)
+            gpu.set_fan_layout(1 if fan == 1 else 0)
+            gpu.set_decode_warp(1 if fan == 2 else 0)
             gpu.set_tuning(0, 0, slices)
             got, st = gpu.replay(p, x, y, yaw, r)
             assert np.array_equal(got, want), ((engine, nw, slices, fan), dict(W=W, H=H, res=res, fov=float(p.fov_deg)), first_diff(got, want))
@@ -873,4 +877,5 @@ def test_random_geometry_and_sensor_constants(gpu, oracle, seed):
     finally:
         gpu.set_engine(0, 0)
         gpu.set_fan_layout(-1)
+        gpu.set_decode_warp(-1)
         gpu.set_tuning(0, 0, 0)

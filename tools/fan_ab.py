@@ -12,12 +12,12 @@ def run(w, label, warps=(0, 4, 8, 16), reps=3):
     g = torch.empty((w.n_flights, p.H, p.W), dtype=torch.int8, device=dev)
     ref = None
     for nw in warps:
-        for fan in (0, 1):
-            m.set_engine(2 if nw else 0, nw); m.set_fan_layout(fan)
+        for fan in (0, 2):                                   # 0 = shared decode, 2 = dedicated decode warp (1 = fan layout: see r2_fan_layout_ab.log)
+            m.set_engine(2 if nw else 0, nw); m.set_fan_layout(1 if fan == 1 else 0); m.set_decode_warp(1 if fan == 2 else 0)
             try:
                 st = m.replay_dev(p, w.n_flights, w.n_frames, *(a.data_ptr() for a in t), g.data_ptr(), want_stats=True)
             except m.UqsError as e:
-                print(f"{label} nw={nw} fan={fan}: {e}"); continue
+                print(f"{label} nw={nw} variant={fan}: {e}"); continue
             m.replay_dev(p, w.n_flights, w.n_frames, *(a.data_ptr() for a in t), g.data_ptr())
             m.set_profiling(True); m.profile_collect()
             for _ in range(reps):
@@ -25,9 +25,9 @@ def run(w, label, warps=(0, 4, 8, 16), reps=3):
             ms, cnt = m.profile_collect(); m.set_profiling(False)
             h = m.grid_hashes_dev(g.data_ptr(), w.n_flights, p.W * p.H).sum(dtype=np.uint64)
             ref = h if ref is None else ref
-            print(f"{label} nw={nw} fan={fan}: setup {ms[1]/reps:.2f} ms replay {ms[2]/reps:.2f} ms  {st['ray_cell_updates']/(ms[2]/reps)/1e6:.0f} G upd/s  "
+            print(f"{label} nw={nw} variant={fan}: setup {ms[1]/reps:.2f} ms replay {ms[2]/reps:.2f} ms  {st['ray_cell_updates']/(ms[2]/reps)/1e6:.0f} G upd/s  "
                   f"{'same bytes' if h == ref else 'DIFFERENT BYTES'}", flush=True)
-    m.set_engine(0, 0); m.set_fan_layout(-1)
+    m.set_engine(0, 0); m.set_fan_layout(-1); m.set_decode_warp(-1)
 
 which = sys.argv[1:] or ["c3", "c5"]
 if "c3" in which:
