@@ -32,7 +32,7 @@ on-chip: {r['onchip_rmw']['achieved_updates_per_s']:.3e} updates/s in the replay
 (`ATOMS.ADD` ceiling {r['onchip_rmw']['atomics_updates_per_s']:.2e}); clocks {D[1]['clocks']['sm_mhz']:.0f} of {D[1]['clocks']['sm_max_mhz']:.0f} MHz, no throttle reason;
 `cpu_baseline` (the reference's own code, {D[1]['cpu_baseline']['cores']} host cores): {D[1]['cpu_baseline']['value']:.2e} updates/s; `--impl reference`: {ref['value']:.2e} on that box, {ref8['value']:.2e} on the {ref8['cpu_baseline']['cores']}-core host of the 8-GPU box.
 Config 4 on eight GPUs: kernels per rank {c48['kernel_ms_per_rank']} ms, step without the gather {c48['ms_per_step_without_gather']:.2f} ms, with it {c48['ms_per_step']:.2f} ms, cuts {D[8]['configs']['c4']['partition'].split('cut at rows ')[1].split(' (')[0]}.
-N=1 from a 1-GPU box, N=2/4/8 from 8-GPU boxes (`r2_bench_n*.json`); the N=2 line predates the send/recv band gather (0.4 ms of its config-4 step).
+N=1 from a 1-GPU box, N=2 from a 2-GPU box, N=4 and N=8 from one 8-GPU box (`r2_bench_n*.json`), all on the final build.
 """
 p = os.path.join(P, "README.md")
 s = open(p).read()
