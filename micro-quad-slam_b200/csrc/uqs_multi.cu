@@ -314,7 +314,9 @@ int uqs_replay_banded_dev(const uqs_params* p, int n_frames, const float* x, con
   if (rows > 0 && (rc = replay_device(dp, 1, n_frames, x, y, yaw, ranges, nullptr, grid, 0, r0, rows, true))) return rc;
   if (gather && (rc = gather_bands(g_ctx, edges, grid, p->W, p->H, g_ctx.stream()))) return rc;
   // every rank's ray set-up sees the whole log, so the counters are the whole log's on every rank
-  return rows > 0 ? fetch_stats(stats, (uint64_t)n_frames) : UQS_OK;
+  if (rows > 0) return fetch_stats(stats, (uint64_t)n_frames);
+  if (stats) memset(stats, 0, sizeof(*stats));       // more ranks than 4-row units: this rank owns nothing
+  return UQS_OK;
 }
 
 /* Host-buffer form for model (i): every rank passes the same log.  Rank r uploads only its 1/N slice over PCIe;
