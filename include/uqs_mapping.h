@@ -141,6 +141,9 @@ int  uqs_set_fan_layout(int on);
  * extra producer warp per CTA does nothing but decode frames into the shared-memory ring, two frames ahead of the
  * consumer warps (4, 8 or 16 of them).  -1 = the built-in choice.  Identical bytes either way. */
 int  uqs_set_decode_warp(int on);
+/* Measurement knob: adds `steps` (0..8) to every frame's collision bound K0 (always safe; identical bytes): what one
+ * collision-checked step per frame costs the resident engine. */
+int  uqs_set_k0_bias(int steps);
 /* Experiment knob for the layouts above: row pitch of the resident box in 32-bit words, modulo 32
  * (-1 = the built-in odd pitch).  Identical bytes for any value. */
 int  uqs_set_resident_pitch_mod(int words_mod32);

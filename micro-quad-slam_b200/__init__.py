@@ -80,7 +80,7 @@ _lib = None
 _EXPORTS = [
     # batch API
     "uqs_params_default", "uqs_init", "uqs_shutdown", "uqs_last_error", "uqs_device_sm_count",
-    "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_set_fan_layout", "uqs_set_decode_warp", "uqs_set_resident_pitch_mod", "uqs_kernel_launches",
+    "uqs_set_stream", "uqs_use_own_stream", "uqs_sync", "uqs_set_tuning", "uqs_set_engine", "uqs_set_fan_layout", "uqs_set_decode_warp", "uqs_set_k0_bias", "uqs_set_resident_pitch_mod", "uqs_kernel_launches",
     "uqs_set_profiling", "uqs_profile_collect", "uqs_profile_timeline", "uqs_set_host_chunk",
     "uqs_pose_integrate", "uqs_pose_integrate_dev", "uqs_replay", "uqs_replay_dev", "uqs_replay_flow",
     "uqs_beam_cells", "uqs_frame_bounds", "uqs_sincosf_batch", "uqs_measure_rmw_peak", "uqs_measure_atoms_peak",
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.uqs_set_fan_layout.argtypes = [ip]
     L.uqs_set_resident_pitch_mod.argtypes = [ip]
     L.uqs_set_decode_warp.argtypes = [ip]
+    L.uqs_set_k0_bias.argtypes = [ip]
     L.uqs_set_profiling.argtypes = [ip]
     L.uqs_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.uqs_profile_timeline.argtypes = [C.POINTER(C.c_double), ip]
@@ -227,6 +228,10 @@ def set_fan_layout(on: int = -1):
 def set_decode_warp(on: int = -1):
     """Resident engine: 1 = a dedicated producer warp decodes frames for the consumer warps, 0 = shared decode, -1 = default."""
     _check(lib().uqs_set_decode_warp(int(on)))
+
+
+def set_k0_bias(steps: int = 0):
+    _check(lib().uqs_set_k0_bias(int(steps)))
 
 
 def set_resident_pitch_mod(words_mod32: int = -1):

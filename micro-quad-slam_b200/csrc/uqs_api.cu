@@ -294,7 +294,7 @@ int replay_device(const DevParams& dp, int n_flights, int n_frames, const float*
     k_ray_setup<<<dim3((unsigned)gpf, (unsigned)nf), 1024, 0, st>>>(
         dp, n_frames, x + fo, y + fo, yaw + fo,
         dp.ranges_u16 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(ranges) + fo * 32) : ranges + fo * 32,
-        kind ? kind + fo : nullptr, may_reside ? 1 : 0,
+        kind ? kind + fo : nullptr, may_reside ? 1 + g_ctx.k0_bias : 0,
         (const uint32_t*)g_ctx.inv_table.p, (uint4*)g_ctx.w->frames.p, (uint2*)g_ctx.w->groups.p, (uint2*)g_ctx.w->rays.p, counters);
     e = cudaGetLastError();
     t_setup.stop();
@@ -658,6 +658,13 @@ int uqs_set_resident_pitch_mod(int words_mod32) {
  * -1 = the built-in choice).  Identical bytes. */
 int uqs_set_decode_warp(int on) {
   g_ctx.flight_prod = on < 0 ? kDefaultDecodeWarp : (on ? 1 : 0);
+  return UQS_OK;
+}
+
+/* Measurement knob: adds `steps` (0..8) to every frame's collision bound K0 (a larger K0 is always safe: more steps
+ * take the collision-checked path).  Prices one collision-checked step per frame in the resident engine. */
+int uqs_set_k0_bias(int steps) {
+  g_ctx.k0_bias = steps < 0 ? 0 : (steps > 8 ? 8 : steps);
   return UQS_OK;
 }
 

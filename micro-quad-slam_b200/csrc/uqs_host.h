@@ -49,6 +49,7 @@ struct Context {
   int tune_sw = 0, tune_sh = 0, tune_slices = 0;
   int engine = 0;                               // 0 auto, 1 warp-owned sub-tiles, 2 grid resident per CTA
   int flight_warps = 0;                         // warps per CTA of the resident engine (0 = 16)
+  int k0_bias = 0;                              // measurement: extra collision-checked steps per frame (uqs_set_k0_bias)
   int pitch_mod = -1;                           // experiment: resident row pitch in words mod 32 (uqs_set_resident_pitch_mod)
   int flight_prod = kDefaultDecodeWarp;         // dedicated decode warp (uqs_set_decode_warp)
   int flight_fan = kDefaultFanLayout;           // lane layout of its free-space steps (uqs_set_fan_layout)
